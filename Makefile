@@ -1,0 +1,58 @@
+# Top-level build: libbgsa_b200.so (CUDA kernels + C ABI, sm_100a only), the C host tools
+# (aligner, convert), the drop-in align_core shims and the test-only host simulator.
+NVCC     ?= nvcc
+GCC      ?= gcc
+ARCH     := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS  := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -Wall -Xcompiler -Wno-unused-function
+CSRC     := bgsa_b200/csrc
+HOST     := bgsa_b200/host
+BUILD    := build
+LIB      := bgsa_b200/libbgsa_b200.so
+
+HDRS := $(wildcard $(CSRC)/*.cuh $(CSRC)/*.h) include/bgsa_b200.h
+
+OBJS := $(BUILD)/api.o $(BUILD)/inst_misc.o $(BUILD)/inst_myers_g.o $(BUILD)/inst_myers_s.o \
+        $(BUILD)/inst_bp_p0.o $(BUILD)/inst_bp_p1.o $(BUILD)/inst_bp_p2.o \
+        $(BUILD)/inst_bp_n0.o $(BUILD)/inst_bp_n1.o $(BUILD)/inst_bp_n2.o
+
+.PHONY: all lib tools sim clean
+all: lib tools sim
+
+lib: $(LIB)
+$(LIB): $(OBJS)
+	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -lcudart
+
+$(BUILD)/api.o: $(CSRC)/api.cu $(HDRS) | $(BUILD)
+	$(NVCC) $(NVFLAGS) -c $< -o $@
+$(BUILD)/inst_misc.o: $(CSRC)/inst_misc.cu $(HDRS) | $(BUILD)
+	$(NVCC) $(NVFLAGS) -c $< -o $@
+$(BUILD)/inst_myers_g.o: $(CSRC)/inst_myers.cu $(HDRS) | $(BUILD)
+	$(NVCC) $(NVFLAGS) -DBGSA_MYERS_MODE=0 -c $< -o $@
+$(BUILD)/inst_myers_s.o: $(CSRC)/inst_myers.cu $(HDRS) | $(BUILD)
+	$(NVCC) $(NVFLAGS) -DBGSA_MYERS_MODE=1 -c $< -o $@
+# BitPAl: one object per (scheme id, packed?) -- keep in sync with BGSA_SCHEMES in instances.h
+$(BUILD)/inst_bp_p0.o: $(CSRC)/inst_bitpal.cu $(HDRS) | $(BUILD)
+	$(NVCC) $(NVFLAGS) -DBGSA_SCHEME_ID=0 -DBGSA_M=2 -DBGSA_I=-3 -DBGSA_G=-5 -DBGSA_PACKED=1 -c $< -o $@
+$(BUILD)/inst_bp_p1.o: $(CSRC)/inst_bitpal.cu $(HDRS) | $(BUILD)
+	$(NVCC) $(NVFLAGS) -DBGSA_SCHEME_ID=1 -DBGSA_M=1 -DBGSA_I=-1 -DBGSA_G=-1 -DBGSA_PACKED=1 -c $< -o $@
+$(BUILD)/inst_bp_p2.o: $(CSRC)/inst_bitpal.cu $(HDRS) | $(BUILD)
+	$(NVCC) $(NVFLAGS) -DBGSA_SCHEME_ID=2 -DBGSA_M=1 -DBGSA_I=-3 -DBGSA_G=-2 -DBGSA_PACKED=1 -c $< -o $@
+$(BUILD)/inst_bp_n0.o: $(CSRC)/inst_bitpal.cu $(HDRS) | $(BUILD)
+	$(NVCC) $(NVFLAGS) -DBGSA_SCHEME_ID=0 -DBGSA_M=2 -DBGSA_I=-3 -DBGSA_G=-5 -DBGSA_PACKED=0 -c $< -o $@
+$(BUILD)/inst_bp_n1.o: $(CSRC)/inst_bitpal.cu $(HDRS) | $(BUILD)
+	$(NVCC) $(NVFLAGS) -DBGSA_SCHEME_ID=1 -DBGSA_M=1 -DBGSA_I=-1 -DBGSA_G=-1 -DBGSA_PACKED=0 -c $< -o $@
+$(BUILD)/inst_bp_n2.o: $(CSRC)/inst_bitpal.cu $(HDRS) | $(BUILD)
+	$(NVCC) $(NVFLAGS) -DBGSA_SCHEME_ID=2 -DBGSA_M=1 -DBGSA_I=-3 -DBGSA_G=-2 -DBGSA_PACKED=0 -c $< -o $@
+
+# test-only: the DP column functions compiled for the HOST (no GPU needed), see tests/host_sim.cu
+sim: tests/libhost_sim.so
+tests/libhost_sim.so: tests/host_sim.cu $(HDRS)
+	$(NVCC) -O2 -std=c++17 -Xcompiler -fPIC -shared -I$(CSRC) -o $@ $<
+
+tools:
+
+$(BUILD):
+	mkdir -p $(BUILD)
+
+clean:
+	rm -rf $(BUILD) $(LIB) tests/libhost_sim.so

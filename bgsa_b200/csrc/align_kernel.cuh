@@ -1,0 +1,172 @@
+// align_kernel.cuh -- the persistent alignment kernel shared by the transposed-DP algorithms
+// (Myers global / semi-global, BitPAl packed / non-packed).
+//
+// An algorithm is a policy class:
+//     static constexpr int K;                         // 32-bit words of the bit-vector PER LANE
+//     struct State;  struct Params;                   // per-lane DP state (registers), constants
+//     static void init(State&);
+//     template <bool CARRY> static uint32_t column(State&, const uint32_t* peq_row, uint32_t cin);
+//         one DP column = one subject base.  With CARRY the low word's carry-ins come from `cin`
+//         (bits 3.. , layout private to the algorithm) and the carry-outs are returned.
+//     static constexpr uint32_t kBoundary;            // carry-in bits at the top row (lane 0)
+//     static Partial partial(const State&, int first_bit, int qlen);   // per-lane score pieces
+//     static int final_score(sum, min_prefix, qlen, slen, Params);     // 32-bit score
+//
+// Thread mapping.  L = lanes per subject (1, 2, 4, 8, 16 or 32); the query bit-vector of L*K words
+// is split into L consecutive segments of K words, one per lane of a group.
+//   L == 1 : one subject per thread (short reads).  No cross-lane traffic at all.
+//   L  > 1 : systolic wavefront inside the warp.  At step t lane r works on column t-r, so the
+//            carries it needs (add carry, shift-in bits) were produced by lane r-1 one step
+//            earlier: ONE __shfl_up_sync per step moves them, together with the subject base,
+//            down the group.  No ballot/carry-lookahead is needed and every lane does full
+//            K-word work; the price is L-1 idle steps per subject (< 1 % for the long sequences
+//            this mode is for).
+//
+// Launch geometry: grid = (persistent CTAs, n_queries), THREADS threads.  Shared memory holds the
+// query's Peq (5 rows) once per CTA and, per warp, a 2-stage buffer of subject tiles filled by
+// 1-D bulk async copies (TMA engine) -- WarpStage in bgsa_common.cuh.  Warps take tiles of 32
+// subjects from a global counter (no tail imbalance, no block-level barrier after start-up).
+// HBM traffic per subject: slen/4 bytes in, 2 bytes out.
+#pragma once
+
+#include "bgsa_common.cuh"
+
+namespace bgsa {
+
+struct Partial { int sum; int minpre; };   // segment sum of deltas, minimum prefix sum inside it
+
+// Row layout of the query Peq in shared/global memory: lane r's K words start at r * KP(K),
+// KP = K rounded up to 4 words so that every lane can use LDS.128.
+__host__ __device__ constexpr int peq_kp(int k) { return (k + 3) / 4 * 4; }
+__host__ __device__ constexpr int peq_row_stride(int k, int lanes) { return peq_stride(peq_kp(k) * lanes); }
+
+template <class Algo, int L, int CH, int THREADS, int UNROLL>
+__global__ void __launch_bounds__(THREADS)
+align_kernel(PackedSubjects ps, const uint32_t *__restrict__ g_peq, int qlen, int16_t *__restrict__ results,
+             long long result_stride, typename Algo::Params prm, unsigned long long *__restrict__ counters) {
+    constexpr int K = Algo::K;
+    constexpr int KP = peq_kp(K);
+    constexpr int STRIDE = peq_row_stride(K, L);
+    constexpr int WARPS = THREADS / 32;
+    constexpr int GROUPS = 32 / L;                 // subjects in flight per warp
+    __shared__ __align__(16) uint32_t s_peq[kPeqRows * STRIDE];
+    __shared__ __align__(128) uint4 s_stage[WARPS * 2 * CH * 32];
+    __shared__ __align__(8) uint64_t s_bar[WARPS * 2];
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int rank = lane % L, group = lane / L;
+    const int q = blockIdx.y;
+    for (int i = threadIdx.x; i < kPeqRows * STRIDE; i += THREADS)
+        s_peq[i] = g_peq[(size_t)q * kPeqRows * STRIDE + i];
+    WarpStage<CH> st;
+    st.init(s_stage + warp * 2 * CH * 32, s_bar + warp * 2, lane);
+    __syncthreads();
+
+    const uint32_t *my_peq = s_peq + rank * KP;
+    unsigned long long *counter = counters + q;
+    int16_t *out = results + (long long)q * result_stride;
+    const int slen = ps.slen, ku = ps.ku;
+    const int nstages = (ku + CH - 1) / CH;
+
+    long long tile = next_tile(counter, lane);
+    int sb = 0;
+    if (tile < ps.ntiles) st.issue(0, ps.codes + tile * ku * 32, min(CH, ku), lane);
+
+    while (tile < ps.ntiles) {
+        const long long nxt = next_tile(counter, lane);
+        const bool with_n = ps.tile_has_n[tile] != 0;
+
+#pragma unroll 1
+        for (int pass = 0; pass < L; pass++) {
+            const int sidx = pass * GROUPS + group;          // subject of this group inside the tile
+            typename Algo::State state;
+            Algo::init(state);
+            uint32_t packet = 0u;                            // what this lane hands to lane rank+1
+            int tcol = -rank;                                // column this lane works on at the next step
+
+            // one wavefront step: receive (base, carries) from the lane above, do one column
+            auto step = [&](uint32_t head_base) {
+                if (L == 1) {
+                    (void)Algo::template column<false>(state, my_peq + head_base * STRIDE, 0u);
+                } else {
+                    uint32_t recv = __shfl_up_sync(0xffffffffu, packet, 1, L);
+                    if (rank == 0) recv = Algo::kBoundary | head_base;
+                    if ((unsigned)tcol < (unsigned)slen)
+                        packet = Algo::template column<true>(state, my_peq + (recv & 7u) * STRIDE, recv) | (recv & 7u);
+                    tcol++;
+                }
+            };
+
+            for (int sg = 0; sg < nstages; sg++) {
+                // prefetch the following stage (same tile & pass, next pass, or next tile)
+                if (sg + 1 < nstages)
+                    st.issue(sb ^ 1, ps.codes + (tile * ku + (long long)(sg + 1) * CH) * 32, min(CH, ku - (sg + 1) * CH), lane);
+                else if (pass + 1 < L)
+                    st.issue(sb ^ 1, ps.codes + tile * ku * 32, min(CH, ku), lane);
+                else if (nxt < ps.ntiles)
+                    st.issue(sb ^ 1, ps.codes + nxt * ku * 32, min(CH, ku), lane);
+                st.wait(sb);
+                const int units = min(CH, ku - sg * CH);
+                for (int u = 0; u < units; u++) {
+                    const uint4 v = st.load(sb, u, sidx);
+                    const int base0 = (sg * CH + u) * kBasesPerUnit;
+                    uint32_t n0 = 0u, n1 = 0u;
+                    if (with_n) {
+                        const int kk = 2 * (sg * CH + u);
+                        n0 = ps.nmask[(tile * ps.kn + kk) * 32 + sidx];
+                        if (kk + 1 < ps.kn) n1 = ps.nmask[(tile * ps.kn + kk + 1) * 32 + sidx];
+                    }
+#pragma unroll
+                    for (int w = 0; w < 4; w++) {
+                        const int nb = min(16, slen - base0 - 16 * w);
+                        uint32_t word = (w == 0) ? v.x : (w == 1) ? v.y : (w == 2) ? v.z : v.w;
+                        if (!with_n) {
+#pragma unroll (UNROLL)
+                            for (int i = 0; i < nb; i++) {
+                                const uint32_t c = word & 3u;
+                                word >>= 2;
+                                step(c);
+                            }
+                        } else {   // rare path: the tile contains at least one 'N'
+                            uint32_t nbits = ((w < 2) ? n0 : n1) >> (16 * (w & 1));
+#pragma unroll 1
+                            for (int i = 0; i < nb; i++) {
+                                const uint32_t c = (word & 3u) | ((nbits & 1u) << 2);
+                                word >>= 2;
+                                nbits >>= 1;
+                                step(c);
+                            }
+                        }
+                    }
+                }
+                __syncwarp();   // every lane has consumed stage sb before it is refilled
+                sb ^= 1;
+            }
+            if (L > 1) {
+#pragma unroll 1
+                for (int i = 0; i < L - 1; i++) step(0u);    // drain the wavefront
+            }
+            // ---- score: combine the per-lane pieces of the final delta vector
+            Partial p = Algo::partial(state, rank * K * 32, qlen);
+            int total = p.sum, best = p.minpre;
+            if (L > 1) {
+                // exclusive prefix of segment sums over the group, then min / total reductions
+                int incl = p.sum;
+#pragma unroll
+                for (int o = 1; o < L; o <<= 1) {
+                    const int up = __shfl_up_sync(0xffffffffu, incl, o, L);
+                    if (rank >= o) incl += up;
+                }
+                best = (incl - p.sum) + p.minpre;
+#pragma unroll
+                for (int o = L >> 1; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o, L));
+                total = __shfl_sync(0xffffffffu, incl, L - 1, L);
+            }
+            const long long subject = tile * kTileSubjects + sidx;
+            if (rank == 0 && subject < ps.count) out[subject] = narrow16(Algo::final_score(total, best, qlen, slen, prm));
+        }
+        tile = nxt;
+    }
+}
+
+}  // namespace bgsa

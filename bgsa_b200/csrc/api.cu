@@ -1,0 +1,423 @@
+// api.cu -- the C ABI of libbgsa_b200.so (include/bgsa_b200.h): argument checking, per-device
+// contexts (streams + grow-only device buffers), host<->device staging and kernel selection.
+// No computation happens on the host besides building the query's match masks (5 x W words).
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "../../include/bgsa_b200.h"
+#include "banded_host.h"
+#include "bitpal.cuh"
+#include "instances.h"
+#include "launch.cuh"
+#include "pack.cuh"
+#include "query_peq.h"
+
+using namespace bgsa;
+
+namespace {
+
+thread_local char g_err[512] = "";
+std::atomic<long long> g_launches{0};
+
+int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define CUDA_TRY(expr)                                                                         \
+    do {                                                                                       \
+        cudaError_t e_ = (expr);                                                               \
+        if (e_ != cudaSuccess)                                                                 \
+            return fail(e_ == cudaErrorMemoryAllocation ? BGSA_ERR_NOMEM : BGSA_ERR_CUDA,      \
+                        "%s failed: %s", #expr, cudaGetErrorString(e_));                       \
+    } while (0)
+
+// ---- instance tables ------------------------------------------------------------------------
+struct KL { int K, L; };
+#define X(k, l) {k, l},
+const KL kMyersTable[] = {BGSA_MYERS_INSTANCES(X)};
+const KL kPackedTable[] = {BGSA_BITPAL_PACKED_INSTANCES(X)};
+const KL kNonPackedTable[] = {BGSA_BITPAL_NONPACKED_INSTANCES(X)};
+#undef X
+struct SchemeRow { int id, M, I, G; };
+#define X(id, m, i, g) {id, m, i, g},
+const SchemeRow kSchemes[] = {BGSA_SCHEMES(X)};
+#undef X
+
+template <size_t N>
+bool pick(const KL (&table)[N], int qlen, KL *out) {
+    for (size_t i = 0; i < N; i++)
+        if (32 * table[i].K * table[i].L >= qlen) { *out = table[i]; return true; }
+    return false;
+}
+int find_scheme(int M, int I, int G) {
+    for (const SchemeRow &s : kSchemes) if (s.M == M && s.I == I && s.G == G) return s.id;
+    return -1;
+}
+
+struct Plan {
+    int algo;
+    KL kl;           // transposed kernels
+    int scheme;      // BitPAl
+    int sign;        // Myers
+    int e;           // banded
+    int layout;      // pack layout the kernel consumes
+    int result_size;
+};
+
+int make_plan(const bgsa_params_t *p, int qlen, int slen, Plan *plan) {
+    if (!p) return fail(BGSA_ERR_ARG, "params is NULL");
+    if (qlen <= 0 || slen <= 0) return fail(BGSA_ERR_ARG, "sequence lengths must be positive (query %d, subject %d)", qlen, slen);
+    plan->algo = p->algo;
+    plan->scheme = -1;
+    plan->sign = p->myers_sign == 0 ? -1 : p->myers_sign;
+    plan->e = p->threshold;
+    plan->layout = LAYOUT_CODES;
+    plan->result_size = 2;
+    plan->kl = KL{0, 0};
+    switch (p->algo) {
+        case BGSA_MYERS_GLOBAL:
+        case BGSA_MYERS_SEMIGLOBAL:
+            if (plan->sign != -1 && plan->sign != 1) return fail(BGSA_ERR_ARG, "myers_sign must be -1, 0 or +1");
+            if (!pick(kMyersTable, qlen, &plan->kl))
+                return fail(BGSA_ERR_UNSUPPORTED, "Myers: query length %d exceeds the largest kernel instance (32768)", qlen);
+            return BGSA_OK;
+        case BGSA_BITPAL_PACKED:
+        case BGSA_BITPAL_NONPACKED: {
+            plan->scheme = find_scheme(p->match, p->mismatch, p->gap);
+            if (plan->scheme < 0)
+                return fail(BGSA_ERR_UNSUPPORTED, "BitPAl: scoring scheme (%d,%d,%d) has no kernel instance (see csrc/instances.h)",
+                            p->match, p->mismatch, p->gap);
+            const bool ok = p->algo == BGSA_BITPAL_PACKED ? pick(kPackedTable, qlen, &plan->kl) : pick(kNonPackedTable, qlen, &plan->kl);
+            if (!ok) return fail(BGSA_ERR_UNSUPPORTED, "BitPAl: query length %d exceeds the largest kernel instance", qlen);
+            return BGSA_OK;
+        }
+        case BGSA_BANDED_MYERS:
+            plan->layout = LAYOUT_PLANES;
+            plan->result_size = 1;
+            if (p->threshold < 1 || p->threshold > 31)
+                return fail(BGSA_ERR_UNSUPPORTED, "banded: threshold %d outside 1..31 (band must fit a 64-bit word)", p->threshold);
+            if (qlen != slen)
+                return fail(BGSA_ERR_UNSUPPORTED, "banded: query (%d) and subject (%d) lengths must be equal", qlen, slen);
+            if (qlen < p->threshold)
+                return fail(BGSA_ERR_UNSUPPORTED, "banded: sequences shorter than the threshold");
+            return BGSA_OK;
+        default:
+            return fail(BGSA_ERR_ARG, "unknown algorithm %d", p->algo);
+    }
+}
+
+// ---- per-device context ----------------------------------------------------------------------
+struct Buf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return BGSA_OK;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) return fail(BGSA_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+        cap = want;
+        return BGSA_OK;
+    }
+};
+struct QueryCache {          // device copy of the query-side tables of the last call
+    Buf d_tab;               // Peq rows, or BandedRow table
+    Buf d_counters;
+    std::vector<char> key;   // (plan, queries) it was built from
+    void *pinned = nullptr;
+    size_t pinned_cap = 0;
+};
+struct Slot {
+    cudaStream_t stream = nullptr;
+    Buf d_rows, d_packed, d_results;
+    QueryCache qc;
+};
+struct DeviceCtx {
+    bool ready = false;
+    int sm_count = 0;
+    Slot slot[2];
+    QueryCache resident_qc;  // bgsa_align_device (caller's stream)
+};
+constexpr int kMaxDevices = 64;
+DeviceCtx g_ctx[kMaxDevices];
+std::mutex g_mu;
+
+int get_ctx(int device, DeviceCtx **out) {
+    if (device < 0 || device >= kMaxDevices) return fail(BGSA_ERR_ARG, "bad device ordinal %d", device);
+    CUDA_TRY(cudaSetDevice(device));
+    std::lock_guard<std::mutex> lk(g_mu);
+    DeviceCtx &c = g_ctx[device];
+    if (!c.ready) {
+        CUDA_TRY(cudaDeviceGetAttribute(&c.sm_count, cudaDevAttrMultiProcessorCount, device));
+        for (Slot &s : c.slot) CUDA_TRY(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+        c.ready = true;
+    }
+    *out = &c;
+    return BGSA_OK;
+}
+
+// Build (or reuse) the query-side tables on the device.  Returns the device pointer in *d_tab.
+int stage_queries(QueryCache &qc, const Plan &plan, const char *queries, int nq, int qlen, int slen, cudaStream_t stream,
+                  const void **d_tab, unsigned long long **d_counters) {
+    const size_t qbytes = (size_t)nq * (qlen + 1);
+    std::vector<char> key(sizeof(Plan) + sizeof(int) * 3 + qbytes);
+    memcpy(key.data(), &plan, sizeof(Plan));
+    const int dims[3] = {nq, qlen, slen};
+    memcpy(key.data() + sizeof(Plan), dims, sizeof(dims));
+    memcpy(key.data() + sizeof(Plan) + sizeof(dims), queries, qbytes);
+    int rc = qc.d_counters.ensure(sizeof(unsigned long long) * (size_t)nq);
+    if (rc) return rc;
+    *d_counters = static_cast<unsigned long long *>(qc.d_counters.p);
+    if (key == qc.key && qc.d_tab.p) { *d_tab = qc.d_tab.p; return BGSA_OK; }
+
+    size_t bytes;
+    if (plan.algo == BGSA_BANDED_MYERS) bytes = sizeof(BandedRowHost) * (size_t)nq * qlen;
+    else bytes = sizeof(uint32_t) * (size_t)nq * kPeqRows * h_peq_row_stride(plan.kl.K, plan.kl.L);
+    if (bytes > qc.pinned_cap) {
+        if (qc.pinned) cudaFreeHost(qc.pinned);
+        qc.pinned = nullptr; qc.pinned_cap = 0;
+        CUDA_TRY(cudaMallocHost(&qc.pinned, bytes + 256));
+        qc.pinned_cap = bytes + 256;
+    } else {
+        // the previous upload from this pinned buffer must have completed before we overwrite it
+        CUDA_TRY(cudaStreamSynchronize(stream));
+    }
+    for (int q = 0; q < nq; q++) {
+        const char *row = queries + (size_t)q * (qlen + 1);
+        if (plan.algo == BGSA_BANDED_MYERS)
+            build_banded_table(row, qlen, slen, plan.e, static_cast<BandedRowHost *>(qc.pinned) + (size_t)q * qlen);
+        else
+            build_query_peq(row, qlen, plan.kl.K, plan.kl.L,
+                            static_cast<uint32_t *>(qc.pinned) + (size_t)q * kPeqRows * h_peq_row_stride(plan.kl.K, plan.kl.L));
+    }
+    rc = qc.d_tab.ensure(bytes);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(qc.d_tab.p, qc.pinned, bytes, cudaMemcpyHostToDevice, stream));
+    qc.key.swap(key);
+    *d_tab = qc.d_tab.p;
+    return BGSA_OK;
+}
+
+int run_align(const Plan &plan, int sm_count, const void *d_tab, unsigned long long *d_counters, int nq, int qlen,
+              const void *d_packed, int slen, int64_t count, void *d_results, int64_t result_stride, cudaStream_t stream) {
+    if (count == 0 || nq == 0) return BGSA_OK;
+    LaunchArgs a;
+    a.ps = make_packed_view(const_cast<void *>(d_packed), slen, count);
+    a.d_peq = static_cast<const uint32_t *>(d_tab);
+    a.n_queries = nq;
+    a.qlen = qlen;
+    a.d_results = d_results;
+    a.result_stride = result_stride;
+    a.d_counters = d_counters;
+    a.sm_count = sm_count;
+    a.stream = stream;
+    cudaError_t e;
+    switch (plan.algo) {
+        case BGSA_MYERS_GLOBAL:     e = launch_myers(0, plan.kl.K, plan.kl.L, a, plan.sign); break;
+        case BGSA_MYERS_SEMIGLOBAL: e = launch_myers(1, plan.kl.K, plan.kl.L, a, plan.sign); break;
+        case BGSA_BITPAL_PACKED:    e = launch_bitpal_packed(plan.scheme, plan.kl.K, plan.kl.L, a); break;
+        case BGSA_BITPAL_NONPACKED: e = launch_bitpal_nonpacked(plan.scheme, plan.kl.K, plan.kl.L, a); break;
+        case BGSA_BANDED_MYERS:     e = launch_banded(a, d_tab, plan.e); break;
+        default: return fail(BGSA_ERR_ARG, "unknown algorithm %d", plan.algo);
+    }
+    if (e != cudaSuccess) return fail(BGSA_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+    g_launches.fetch_add(1);
+    return BGSA_OK;
+}
+
+}  // namespace
+
+// ================================================================================================
+extern "C" {
+
+const char *bgsa_version(void) { return "bgsa_b200 0.1 (sm_100a)"; }
+const char *bgsa_last_error(void) { return g_err; }
+
+int bgsa_device_count(int *count) {
+    if (!count) return fail(BGSA_ERR_ARG, "count is NULL");
+    CUDA_TRY(cudaGetDeviceCount(count));
+    return BGSA_OK;
+}
+
+void bgsa_params_default(bgsa_params_t *p, int algo) {
+    if (!p) return;
+    p->algo = algo;
+    p->match = 2; p->mismatch = -3; p->gap = -5;   // original/BGSA_AVX512/align_core.c:13-15
+    if (algo == BGSA_MYERS_GLOBAL || algo == BGSA_MYERS_SEMIGLOBAL || algo == BGSA_BANDED_MYERS) {
+        p->match = 0; p->mismatch = -1; p->gap = -1;   // Main.java:253-257
+    }
+    p->threshold = 31;                              // banded/BGSA_CPU/main.c:43
+    p->myers_sign = -1;                             // generator -m 0
+}
+
+int bgsa_result_size(int algo) { return algo == BGSA_BANDED_MYERS ? 1 : 2; }
+
+int bgsa_supported(const bgsa_params_t *p, int query_len, int subject_len) {
+    Plan plan;
+    return make_plan(p, query_len, subject_len, &plan);
+}
+
+int bgsa_kernel_name(const bgsa_params_t *p, int query_len, int subject_len, char *buf, int buflen) {
+    Plan plan;
+    int rc = make_plan(p, query_len, subject_len, &plan);
+    if (rc) return rc;
+    if (!buf || buflen <= 0) return fail(BGSA_ERR_ARG, "buf is NULL");
+    switch (plan.algo) {
+        case BGSA_MYERS_GLOBAL: snprintf(buf, buflen, "align_kernel<MyersAlgo<K=%d,global>,L=%d>", plan.kl.K, plan.kl.L); break;
+        case BGSA_MYERS_SEMIGLOBAL: snprintf(buf, buflen, "align_kernel<MyersAlgo<K=%d,semiglobal>,L=%d>", plan.kl.K, plan.kl.L); break;
+        case BGSA_BITPAL_PACKED: snprintf(buf, buflen, "align_kernel<BitpalPacked<%d,%d,%d,K=%d>,L=%d>", p->match, p->mismatch, p->gap, plan.kl.K, plan.kl.L); break;
+        case BGSA_BITPAL_NONPACKED: snprintf(buf, buflen, "align_kernel<BitpalNonPacked<%d,%d,%d,K=%d>,L=%d>", p->match, p->mismatch, p->gap, plan.kl.K, plan.kl.L); break;
+        default: snprintf(buf, buflen, "banded_kernel<%s>", 2 * plan.e + 2 <= 32 ? "u32" : "u64"); break;
+    }
+    return BGSA_OK;
+}
+
+int64_t bgsa_launch_count(void) { return g_launches.load(); }
+
+void *bgsa_malloc_host(size_t bytes) {
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { fail(BGSA_ERR_NOMEM, "cudaMallocHost(%zu) failed", bytes); return nullptr; }
+    return p;
+}
+void bgsa_free_host(void *p) { if (p) cudaFreeHost(p); }
+
+int64_t bgsa_packed_bytes(int subject_len, int64_t count) {
+    if (subject_len <= 0 || count < 0) return -1;
+    return packed_bytes(subject_len, count);
+}
+
+int bgsa_pack_subjects_device(const bgsa_params_t *p, const void *d_rows, int subject_len, int64_t count, void *d_packed,
+                              int device, void *stream) {
+    if (!p || (!d_rows && count > 0) || (!d_packed && count > 0) || subject_len <= 0 || count < 0)
+        return fail(BGSA_ERR_ARG, "bgsa_pack_subjects_device: bad argument");
+    DeviceCtx *ctx;
+    int rc = get_ctx(device, &ctx);
+    if (rc) return rc;
+    if (count == 0) return BGSA_OK;
+    const int layout = p->algo == BGSA_BANDED_MYERS ? LAYOUT_PLANES : LAYOUT_CODES;
+    cudaError_t e = launch_pack(layout, d_rows, subject_len, count, d_packed, ctx->sm_count, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return fail(BGSA_ERR_CUDA, "pack kernel launch failed: %s", cudaGetErrorString(e));
+    g_launches.fetch_add(1);
+    return BGSA_OK;
+}
+
+int bgsa_align_device(const bgsa_params_t *p, const char *h_queries, int n_queries, int query_len, const void *d_packed,
+                      int subject_len, int64_t count, void *d_results, int64_t result_stride, int device, void *stream) {
+    Plan plan;
+    int rc = make_plan(p, query_len, subject_len, &plan);
+    if (rc) return rc;
+    if (!h_queries || n_queries < 0 || count < 0 || (count > 0 && (!d_packed || !d_results)) || result_stride < count)
+        return fail(BGSA_ERR_ARG, "bgsa_align_device: bad argument");
+    DeviceCtx *ctx;
+    rc = get_ctx(device, &ctx);
+    if (rc) return rc;
+    if (count == 0 || n_queries == 0) return BGSA_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const void *d_tab; unsigned long long *d_counters;
+    rc = stage_queries(ctx->resident_qc, plan, h_queries, n_queries, query_len, subject_len, st, &d_tab, &d_counters);
+    if (rc) return rc;
+    return run_align(plan, ctx->sm_count, d_tab, d_counters, n_queries, query_len, d_packed, subject_len, count, d_results,
+                     result_stride, st);
+}
+
+int bgsa_align_batch_submit(const bgsa_params_t *p, const char *queries, int n_queries, int query_len,
+                            const bgsa_seq_t *subjects, int64_t first, int64_t count, void *results, int64_t result_stride,
+                            int device, int slot) {
+    if (!subjects) return fail(BGSA_ERR_ARG, "subjects is NULL");
+    Plan plan;
+    int rc = make_plan(p, query_len, subjects->len, &plan);
+    if (rc) return rc;
+    if (!queries || n_queries < 0 || first < 0 || count < 0 || first + count > subjects->count || slot < 0 || slot > 1 ||
+        (count > 0 && n_queries > 0 && (!results || !subjects->content)) || result_stride < count)
+        return fail(BGSA_ERR_ARG, "bgsa_align_batch: bad argument (first %lld count %lld of %lld, stride %lld)",
+                    (long long)first, (long long)count, (long long)subjects->count, (long long)result_stride);
+    DeviceCtx *ctx;
+    rc = get_ctx(device, &ctx);
+    if (rc) return rc;
+    if (count == 0 || n_queries == 0) return BGSA_OK;
+    Slot &s = ctx->slot[slot];
+    const int slen = subjects->len;
+    const size_t row_bytes = (size_t)count * (slen + 1);
+    const size_t esize = plan.result_size;
+    if ((rc = s.d_rows.ensure(row_bytes + 16))) return rc;
+    if ((rc = s.d_packed.ensure((size_t)packed_bytes(slen, count)))) return rc;
+    if ((rc = s.d_results.ensure(esize * (size_t)n_queries * (size_t)count))) return rc;
+    // host -> device: the ASCII rows exactly as file.c:44-115 left them
+    CUDA_TRY(cudaMemcpyAsync(s.d_rows.p, subjects->content + (size_t)first * (slen + 1), row_bytes, cudaMemcpyHostToDevice, s.stream));
+    cudaError_t e = launch_pack(plan.layout, s.d_rows.p, slen, count, s.d_packed.p, ctx->sm_count, s.stream);
+    if (e != cudaSuccess) return fail(BGSA_ERR_CUDA, "pack kernel launch failed: %s", cudaGetErrorString(e));
+    g_launches.fetch_add(1);
+    const void *d_tab; unsigned long long *d_counters;
+    rc = stage_queries(s.qc, plan, queries, n_queries, query_len, slen, s.stream, &d_tab, &d_counters);
+    if (rc) return rc;
+    rc = run_align(plan, ctx->sm_count, d_tab, d_counters, n_queries, query_len, s.d_packed.p, slen, count, s.d_results.p, count, s.stream);
+    if (rc) return rc;
+    // device -> host: [query][subject] rows into the caller's (possibly wider) result matrix
+    CUDA_TRY(cudaMemcpy2DAsync(results, esize * (size_t)result_stride, s.d_results.p, esize * (size_t)count, esize * (size_t)count,
+                               (size_t)n_queries, cudaMemcpyDeviceToHost, s.stream));
+    return BGSA_OK;
+}
+
+int bgsa_align_batch_wait(int device, int slot) {
+    if (slot < 0 || slot > 1) return fail(BGSA_ERR_ARG, "slot must be 0 or 1");
+    DeviceCtx *ctx;
+    int rc = get_ctx(device, &ctx);
+    if (rc) return rc;
+    CUDA_TRY(cudaStreamSynchronize(ctx->slot[slot].stream));
+    return BGSA_OK;
+}
+
+int bgsa_align_batch(const bgsa_params_t *p, const char *queries, int n_queries, int query_len, const bgsa_seq_t *subjects,
+                     int64_t first, int64_t count, void *results, int64_t result_stride, int device) {
+    int rc = bgsa_align_batch_submit(p, queries, n_queries, query_len, subjects, first, count, results, result_stride, device, 0);
+    if (rc) return rc;
+    return bgsa_align_batch_wait(device, 0);
+}
+
+int bgsa_int_peak(int device, double *lane_ops_per_s, double *sm_clock_mhz) {
+    if (!lane_ops_per_s) return fail(BGSA_ERR_ARG, "lane_ops_per_s is NULL");
+    DeviceCtx *ctx;
+    int rc = get_ctx(device, &ctx);
+    if (rc) return rc;
+    unsigned int *d_sink;
+    CUDA_TRY(cudaMalloc(&d_sink, 64));
+    CUDA_TRY(cudaMemset(d_sink, 0, 64));
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    cudaStream_t st = ctx->slot[0].stream;
+    const int iters = 20000;
+    double best = 0.0, best_mhz = 0.0;
+    for (int rep = 0; rep < 4; rep++) {           // rep 0 = warm-up
+        CUDA_TRY(cudaEventRecord(e0, st));
+        cudaError_t e = launch_int_peak(ctx->sm_count, iters, d_sink, st);
+        if (e != cudaSuccess) return fail(BGSA_ERR_CUDA, "int_peak launch failed: %s", cudaGetErrorString(e));
+        g_launches.fetch_add(1);
+        CUDA_TRY(cudaEventRecord(e1, st));
+        CUDA_TRY(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        long long cycles = 0;
+        CUDA_TRY(cudaMemcpy(&cycles, d_sink + 2, sizeof(cycles), cudaMemcpyDeviceToHost));
+        const double ops = (double)ctx->sm_count * 8 * 256 * (double)iters * 64.0;
+        const double rate = ops / (ms * 1e-3);
+        if (rep > 0 && rate > best) { best = rate; best_mhz = (double)cycles / (ms * 1e3); }
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d_sink);
+    *lane_ops_per_s = best;
+    if (sm_clock_mhz) *sm_clock_mhz = best_mhz;
+    return BGSA_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,356 @@
+// bitpal.cuh -- BitPAl (Loving, Hernandez, Benson) bit-parallel global alignment with general
+// integer scores (match M, mismatch I, gap G), as tps_kernel policies.
+//
+// Replaces the generated align_mic / align_avx (original/BGSA_AVX512/align_core.c:19-485,
+// original/BGSA_AVX2/align_core.c) and what BitPAlGenerator.java emits for other (M,I,G)
+// (:151-534 packed, :1392-1701 non-packed).  Scoring schemes are template instances.
+//
+// The recurrence we implement (derived from the NW recurrence; the reference's generated code
+// evaluates the same quantities).  With p the position along the bit-vector
+// (here: the QUERY), one DP column per subject base, and after subtracting G from every delta:
+//     d_p = (S[p][t] - S[p-1][t]) - G        state, in [0, A]          A = M - 2G
+//     e_p = (S[p][t+1] - S[p][t]) - G        within the column, e_0 = 0 (global top row)
+//     w_p = A on a match, B on a mismatch                               B = max(I - 2G, 0)
+//     y_p = max(w_p, e_{p-1})
+//     e_p = max(0, y_p - d_p)
+//     T_p = max(y_p, d_p)                    (= diagonal difference - 2G)
+//     d'_p = T_p - e_{p-1}
+// The serial dependency e_{p-1} -> e_p only matters for the "high" classes e in (B, A]: they
+// propagate unchanged through runs of d = 0 on mismatches, which one integer ADD per class
+// resolves for 32 positions at once (carry propagation = run propagation), exactly BitPAl's trick.
+//
+// "packed"     : d kept as NB = ceil(log2(A+1)) binary bit-planes (reference: two's complement of
+//                -d in NB+1 planes); y, e, T as binary planes; bit-sliced subtract/compare.
+// "non-packed" : d kept one-hot, one bit-vector per value 0..A (BitPAl's original formulation).
+// Final score = G*(n+m) + sum_p d_p, times the common factor the scores were divided by
+// (Main.java:213-267, BitPAlGenerator.java:124-130), low 32 bits narrowed to int16.
+#pragma once
+
+#include "align_kernel.cuh"
+
+namespace bgsa {
+
+constexpr int cgcd(int a, int b) { return b == 0 ? a : cgcd(b, a % b); }
+constexpr int cabs(int a) { return a < 0 ? -a : a; }
+constexpr int cbits(int v) { int b = 0; while ((1 << b) < v + 1) b++; return b; }   // bits to hold 0..v
+
+// Main.java:213-238 picks the largest i <= min(|scores|) dividing all three (0 match is skipped).
+constexpr int common_factor(int M, int I, int G) {
+    int m = cabs(I), g = cabs(G);
+    int mn = M == 0 ? m : M;
+    if (m < mn) mn = m;
+    if (g < mn) mn = g;
+    int f = 1;
+    for (int i = 2; i <= mn; i++) if (M % i == 0 && m % i == 0 && g % i == 0) f = i;
+    return f;
+}
+
+template <int M_, int I_, int G_>
+struct Scheme {
+    static constexpr int F = common_factor(M_, I_, G_);
+    static constexpr int M = M_ / F, I = I_ / F, G = G_ / F;
+    static constexpr int A = M - 2 * G;
+    static constexpr int B = (I - 2 * G) > 0 ? (I - 2 * G) : 0;
+    static constexpr int NH = A - B;          // number of high classes B+1 .. A
+    static constexpr int NB = cbits(A);       // binary planes for 0..A
+    static_assert(G_ < 0 && M_ > I_ && M_ >= 0 && A >= 1 && B < A, "unsupported scoring scheme");
+};
+
+struct BitpalParams { int dummy; };
+
+// ---------------------------------------------------------------------------------------------
+// packed
+// ---------------------------------------------------------------------------------------------
+template <class S, int K_>
+struct BitpalPacked {
+    static constexpr int K = K_;
+    static constexpr int A = S::A, B = S::B, NB = S::NB, NH = S::NH;
+    using Params = BitpalParams;
+    struct State { uint32_t d[NB][K]; };
+
+    static BGSA_HD void init(State &s) {
+#pragma unroll
+        for (int b = 0; b < NB; b++)
+#pragma unroll
+            for (int j = 0; j < K; j++) s.d[b][j] = 0u;      // global start: every delta = G
+    }
+
+    // carry word layout (bits above the 3-bit base): NH add carries (chain c at bit 3+c), NH-1
+    // shift-in bits of the init vectors (class c at bit 3+NH+c), NB shift-in bits of the e planes.
+    static constexpr int kAddBit = 3, kInitBit = 3 + NH, kEBit = 3 + NH + (NH > 0 ? NH - 1 : 0);
+    static_assert(kEBit + NB <= 32, "carry word overflow");
+    static constexpr uint32_t kBoundary = 0u;            // global top row: e_0 = 0, nothing propagates in
+
+    template <bool CARRY>
+    static BGSA_HD uint32_t column(State &s, const uint32_t *row, uint32_t cin) {
+        uint32_t cout = 0u;
+        uint32_t eq[(K + 3) / 4 * 4];
+#pragma unroll
+        for (int j = 0; j < (K + 3) / 4; j++) {
+            const uint4 v = reinterpret_cast<const uint4 *>(row)[j];
+            eq[4 * j] = v.x; eq[4 * j + 1] = v.y; eq[4 * j + 2] = v.z; eq[4 * j + 3] = v.w;
+        }
+        // ---- decode the d classes the chains need: Z = [d == 0], D[v] = [d == v], v = 1..NH-1
+        uint32_t Z[K], remain[K];
+        uint32_t D[NH > 1 ? NH : 1][K];
+#pragma unroll
+        for (int j = 0; j < K; j++) {
+            uint32_t any = 0u;
+#pragma unroll
+            for (int b = 0; b < NB; b++) any |= s.d[b][j];
+            Z[j] = ~any;
+            remain[j] = Z[j] & ~eq[j];                       // d == 0 and mismatch: runs that propagate
+#pragma unroll
+            for (int v = 1; v < NH; v++) {
+                uint32_t m = 0xffffffffu;
+#pragma unroll
+                for (int b = 0; b < NB; b++) m &= ((v >> b) & 1) ? s.d[b][j] : ~s.d[b][j];
+                D[v][j] = m;
+            }
+        }
+        // ---- high classes, top down.  Y[c][j] = [y_p == B+1+c]   (c = NH-1 is class A)
+        uint32_t Y[NH > 0 ? NH : 1][K];
+        if (NH > 0) {
+            uint32_t a0[K], sum[K];
+#pragma unroll
+            for (int j = 0; j < K; j++) a0[j] = Z[j] & eq[j];
+            const uint32_t co = add_chain<K, CARRY, CARRY>(sum, a0, Z, cin & (1u << (kAddBit + NH - 1)));
+            if (CARRY) cout |= co << (kAddBit + NH - 1);
+#pragma unroll
+            for (int j = 0; j < K; j++) Y[NH - 1][j] = (sum[j] ^ remain[j]) | eq[j];   // e_{p-1} == A, or match
+#pragma unroll
+            for (int c = NH - 2; c >= 0; c--) {               // class k = B+1+c
+                uint32_t init[K], sh[K];
+#pragma unroll
+                for (int j = 0; j < K; j++) {
+                    uint32_t v = 0u;
+#pragma unroll
+                    for (int dl = 1; c + dl <= NH - 1; dl++) v |= D[dl][j] & Y[c + dl][j];
+                    init[j] = v;                              // e_p == k at a position with d != 0
+                }
+#pragma unroll
+                for (int j = 0; j < K; j++)
+                    sh[j] = shl1_carry(j ? init[j - 1] : (CARRY ? cin << (31 - (kInitBit + c)) : 0u), init[j]);
+                const uint32_t co2 = add_chain<K, CARRY, CARRY>(sum, sh, remain, cin & (1u << (kAddBit + c)));
+                if (CARRY) cout |= (co2 << (kAddBit + c)) | ((init[K - 1] >> 31) << (kInitBit + c));
+#pragma unroll
+                for (int j = 0; j < K; j++) Y[c][j] = (sum[j] ^ remain[j]) & ~eq[j];
+            }
+        }
+        // ---- binary planes of y, then e = max(0, y - d), T = max(y, d), d' = T - (e << 1)
+        uint32_t e_prev[NB];
+#pragma unroll
+        for (int b = 0; b < NB; b++) e_prev[b] = CARRY ? cin << (31 - (kEBit + b)) : 0u;   // e_0 = 0: global top row
+#pragma unroll
+        for (int j = 0; j < K; j++) {
+            uint32_t hi = 0u;
+#pragma unroll
+            for (int c = 0; c < NH; c++) hi |= Y[c][j];
+            uint32_t y[NB];
+#pragma unroll
+            for (int b = 0; b < NB; b++) {
+                uint32_t v = ((B >> b) & 1) ? ~hi : 0u;
+#pragma unroll
+                for (int c = 0; c < NH; c++) if (((B + 1 + c) >> b) & 1) v |= Y[c][j];
+                y[b] = v;
+            }
+            // borrow chain of y - d
+            uint32_t diff[NB], br = 0u;
+#pragma unroll
+            for (int b = 0; b < NB; b++) {
+                const uint32_t yb = y[b], db = s.d[b][j];
+                diff[b] = yb ^ db ^ br;
+                br = (~yb & db) | (~(yb ^ db) & br);
+            }
+            const uint32_t lt = br;                           // y < d
+            uint32_t e[NB], T[NB];
+#pragma unroll
+            for (int b = 0; b < NB; b++) {
+                e[b] = diff[b] & ~lt;
+                T[b] = (lt & s.d[b][j]) | (~lt & y[b]);
+            }
+            // shift e one position up (e_{p-1} aligned with p), then d' = T - es
+            uint32_t br2 = 0u;
+#pragma unroll
+            for (int b = 0; b < NB; b++) {
+                const uint32_t es = shl1_carry(e_prev[b], e[b]);
+                e_prev[b] = e[b];
+                const uint32_t tb = T[b];
+                s.d[b][j] = tb ^ es ^ br2;
+                br2 = (~tb & es) | (~(tb ^ es) & br2);
+            }
+        }
+        if (CARRY) {
+#pragma unroll
+            for (int b = 0; b < NB; b++) cout |= (e_prev[b] >> 31) << (kEBit + b);
+        }
+        return cout;
+    }
+
+    static BGSA_HD Partial partial(const State &s, int first_bit, int qlen) {
+        Partial r; r.sum = 0; r.minpre = 0;
+#pragma unroll
+        for (int j = 0; j < K; j++) {
+            const int rem = qlen - first_bit - 32 * j;
+            const uint32_t mask = rem >= 32 ? 0xffffffffu : (rem <= 0 ? 0u : ((1u << rem) - 1u));
+#pragma unroll
+            for (int b = 0; b < NB; b++) r.sum += popc32(s.d[b][j] & mask) << b;
+        }
+        return r;
+    }
+    static BGSA_HD int final_score(int sum, int, int qlen, int slen, Params) {
+        return (S::G * (qlen + slen) + sum) * S::F;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// non-packed: one bit-vector per value of d (BitPAlGenerator.java:1392-1701 keeps dh_min..dh_max;
+// we keep the A vectors for d = 1..A, d == 0 being their complement).
+// ---------------------------------------------------------------------------------------------
+template <class S, int K_>
+struct BitpalNonPacked {
+    static constexpr int K = K_;
+    static constexpr int A = S::A, B = S::B, NH = S::NH;
+    using Params = BitpalParams;
+    struct State { uint32_t d[A][K]; };        // d[v-1][j] = [d == v]
+
+    static BGSA_HD void init(State &s) {
+#pragma unroll
+        for (int v = 0; v < A; v++)
+#pragma unroll
+            for (int j = 0; j < K; j++) s.d[v][j] = 0u;
+    }
+
+    // carry word layout: add carry of class k (B < k <= A) at bit 3 + (k-B-1); shift-in bit of
+    // the init vector of class k (1 <= k < A) at bit 3 + NH + (k-1).
+    static constexpr int kAddBit = 3, kInitBit = 3 + NH;
+    static_assert(kInitBit + A - 1 <= 32, "carry word overflow");
+    static constexpr uint32_t kBoundary = 0u;
+
+    template <bool CARRY>
+    static BGSA_HD uint32_t column(State &s, const uint32_t *row, uint32_t cin) {
+        uint32_t cout = 0u;
+        uint32_t eq[(K + 3) / 4 * 4];
+#pragma unroll
+        for (int j = 0; j < (K + 3) / 4; j++) {
+            const uint4 v = reinterpret_cast<const uint4 *>(row)[j];
+            eq[4 * j] = v.x; eq[4 * j + 1] = v.y; eq[4 * j + 2] = v.z; eq[4 * j + 3] = v.w;
+        }
+        uint32_t Z[K], remain[K];
+#pragma unroll
+        for (int j = 0; j < K; j++) {
+            uint32_t any = 0u;
+#pragma unroll
+            for (int v = 0; v < A; v++) any |= s.d[v][j];
+            Z[j] = ~any;
+            remain[j] = Z[j] & ~eq[j];
+        }
+        // DV(v, j) = [d_p == v]
+#define DV(v, j) (((v) == 0) ? Z[j] : s.d[((v) > 0 ? (v) : 1) - 1][j])
+#define SHIFT_IN(k) (CARRY ? cin << (31 - (kInitBit + (k) - 1)) : 0u)
+        // X[v][j] = [e_{p-1} == v] for v = 1..A (shifted form), built class by class.
+        // [y_p == v]: v == A -> X[A] | match ; B < v < A -> X[v] & ~match ; v == B -> rest.
+        uint32_t X[A + 1][K];
+        {
+            uint32_t a0[K], sum[K];
+#pragma unroll
+            for (int j = 0; j < K; j++) a0[j] = Z[j] & eq[j];
+            const uint32_t co = add_chain<K, CARRY, CARRY>(sum, a0, Z, cin & (1u << (kAddBit + NH - 1)));
+            if (CARRY) cout |= co << (kAddBit + NH - 1);
+#pragma unroll
+            for (int j = 0; j < K; j++) X[A][j] = sum[j] ^ remain[j];
+#pragma unroll
+            for (int k = A - 1; k > B; k--) {
+                uint32_t init[K], sh[K];
+#pragma unroll
+                for (int j = 0; j < K; j++) {
+                    uint32_t v = DV(A - k, j) & (X[A][j] | eq[j]);
+#pragma unroll
+                    for (int h = A - 1; h > k; h--) v |= DV(h - k, j) & (X[h][j] & ~eq[j]);
+                    init[j] = v;
+                }
+#pragma unroll
+                for (int j = 0; j < K; j++) sh[j] = shl1_carry(j ? init[j - 1] : SHIFT_IN(k), init[j]);
+                const uint32_t co2 = add_chain<K, CARRY, CARRY>(sum, sh, remain, cin & (1u << (kAddBit + k - B - 1)));
+                if (CARRY) cout |= (co2 << (kAddBit + k - B - 1)) | ((init[K - 1] >> 31) << (kInitBit + k - 1));
+#pragma unroll
+                for (int j = 0; j < K; j++) X[k][j] = sum[j] ^ remain[j];
+            }
+        }
+        uint32_t rest[K];
+#pragma unroll
+        for (int j = 0; j < K; j++) {
+            uint32_t any = X[A][j] | eq[j];
+#pragma unroll
+            for (int k = A - 1; k > B; k--) any |= X[k][j];
+            rest[j] = ~any;
+        }
+        // low classes 1..B: e_p == k  <=>  y_p - d_p == k ; no propagation, plain shift
+#pragma unroll
+        for (int k = B; k >= 1; k--) {
+            uint32_t init[K];
+#pragma unroll
+            for (int j = 0; j < K; j++) {
+                uint32_t v = DV(A - k, j) & (X[A][j] | eq[j]);
+#pragma unroll
+                for (int h = A - 1; h > B; h--) v |= DV(h - k, j) & (X[h][j] & ~eq[j]);
+                v |= DV(B - k, j) & rest[j];
+                init[j] = v;
+            }
+            if (CARRY) cout |= (init[K - 1] >> 31) << (kInitBit + k - 1);
+#pragma unroll
+            for (int j = 0; j < K; j++) X[k][j] = shl1_carry(j ? init[j - 1] : SHIFT_IN(k), init[j]);
+        }
+#undef DV
+#undef SHIFT_IN
+        // X0 = [e_{p-1} == 0]
+        uint32_t X0[K];
+#pragma unroll
+        for (int j = 0; j < K; j++) {
+            uint32_t any = 0u;
+#pragma unroll
+            for (int k = 1; k <= A; k++) any |= X[k][j];
+            X0[j] = ~any;
+        }
+        // Mx(v) = [max(w, d) == v]: v == A -> d==A | match ; B < v < A -> d==v & ~match ; v == B -> others
+        // d'_k = OR_{m >= max(k,B)} Mx(m) & [e_{p-1} == m - k]      (k >= 1)
+#pragma unroll
+        for (int j = 0; j < K; j++) {
+            uint32_t mx[A + 1];
+            uint32_t any = 0u;
+            mx[A] = s.d[A - 1][j] | eq[j];
+            any |= mx[A];
+#pragma unroll
+            for (int v = A - 1; v > B; v--) { mx[v] = s.d[v - 1][j] & ~eq[j]; any |= mx[v]; }
+            mx[B] = ~any;
+            uint32_t nd[A];
+#pragma unroll
+            for (int k = 1; k <= A; k++) {
+                uint32_t v = 0u;
+#pragma unroll
+                for (int m = (k > B ? k : B); m <= A; m++) v |= mx[m] & ((m - k) == 0 ? X0[j] : X[(m - k) > 0 ? (m - k) : 1][j]);
+                nd[k - 1] = v;
+            }
+#pragma unroll
+            for (int k = 0; k < A; k++) s.d[k][j] = nd[k];
+        }
+        return cout;
+    }
+
+    static BGSA_HD Partial partial(const State &s, int first_bit, int qlen) {
+        Partial r; r.sum = 0; r.minpre = 0;
+#pragma unroll
+        for (int j = 0; j < K; j++) {
+            const int rem = qlen - first_bit - 32 * j;
+            const uint32_t mask = rem >= 32 ? 0xffffffffu : (rem <= 0 ? 0u : ((1u << rem) - 1u));
+#pragma unroll
+            for (int v = 1; v <= A; v++) r.sum += v * popc32(s.d[v - 1][j] & mask);
+        }
+        return r;
+    }
+    static BGSA_HD int final_score(int sum, int, int qlen, int slen, Params) {
+        return (S::G * (qlen + slen) + sum) * S::F;
+    }
+};
+
+}  // namespace bgsa

@@ -1,0 +1,36 @@
+// inst_bitpal.cu -- BitPAl kernel instances for ONE scoring scheme and ONE state encoding
+// (compiled once per (scheme, packed?) so that the heavy instances build in parallel).
+#include "instances.h"
+#include "launch.cuh"
+#include "bitpal.cuh"
+
+namespace bgsa {
+
+#if !defined(BGSA_SCHEME_ID) || !defined(BGSA_M) || !defined(BGSA_I) || !defined(BGSA_G) || !defined(BGSA_PACKED)
+#error "compile with -DBGSA_SCHEME_ID= -DBGSA_M= -DBGSA_I= -DBGSA_G= -DBGSA_PACKED="
+#endif
+
+#define BGSA_CAT_(a, b) a##b
+#define BGSA_CAT(a, b) BGSA_CAT_(a, b)
+
+using TheScheme = Scheme<BGSA_M, BGSA_I, BGSA_G>;
+
+#if BGSA_PACKED
+cudaError_t BGSA_CAT(launch_bitpal_packed_s, BGSA_SCHEME_ID)(int K, int L, const LaunchArgs &a) {
+#define X(k, l) \
+    if (K == k && L == l) return launch_align<BitpalPacked<TheScheme, k>, l, 2>(a, BitpalParams{0});
+    BGSA_BITPAL_PACKED_INSTANCES(X)
+#undef X
+    return cudaErrorInvalidValue;
+}
+#else
+cudaError_t BGSA_CAT(launch_bitpal_nonpacked_s, BGSA_SCHEME_ID)(int K, int L, const LaunchArgs &a) {
+#define X(k, l) \
+    if (K == k && L == l) return launch_align<BitpalNonPacked<TheScheme, k>, l, 1>(a, BitpalParams{0});
+    BGSA_BITPAL_NONPACKED_INSTANCES(X)
+#undef X
+    return cudaErrorInvalidValue;
+}
+#endif
+
+}  // namespace bgsa

@@ -1,0 +1,131 @@
+// inst_misc.cu -- banded kernel instances, pack / unpeq kernels, algorithm dispatchers and the
+// INT32-pipe throughput probe.
+#include "banded.cuh"
+#include "instances.h"
+#include "launch.cuh"
+#include "pack.cuh"
+
+namespace bgsa {
+
+// ---- dispatch over the per-file instance launchers ------------------------------------------
+cudaError_t launch_myers_global(int K, int L, const LaunchArgs &a, int sign);
+cudaError_t launch_myers_semiglobal(int K, int L, const LaunchArgs &a, int sign);
+#define X(id, m, i, g)                                                              \
+    cudaError_t launch_bitpal_packed_s##id(int K, int L, const LaunchArgs &a);     \
+    cudaError_t launch_bitpal_nonpacked_s##id(int K, int L, const LaunchArgs &a);
+BGSA_SCHEMES(X)
+#undef X
+
+cudaError_t launch_myers(int mode, int K, int L, const LaunchArgs &a, int sign) {
+    return mode == 0 ? launch_myers_global(K, L, a, sign) : launch_myers_semiglobal(K, L, a, sign);
+}
+cudaError_t launch_bitpal_packed(int scheme, int K, int L, const LaunchArgs &a) {
+#define X(id, m, i, g) if (scheme == id) return launch_bitpal_packed_s##id(K, L, a);
+    BGSA_SCHEMES(X)
+#undef X
+    return cudaErrorInvalidValue;
+}
+cudaError_t launch_bitpal_nonpacked(int scheme, int K, int L, const LaunchArgs &a) {
+#define X(id, m, i, g) if (scheme == id) return launch_bitpal_nonpacked_s##id(K, L, a);
+    BGSA_SCHEMES(X)
+#undef X
+    return cudaErrorInvalidValue;
+}
+
+// ---- banded ------------------------------------------------------------------------------------
+template <bool WIDE>
+static cudaError_t launch_banded_t(const LaunchArgs &a, const void *d_rows_table, int e) {
+    constexpr int THREADS = 128;
+    auto kern = banded_kernel<WIDE, THREADS>;
+    static int occ = 0;
+    if (occ == 0) {
+        cudaError_t err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, 0);
+        if (err != cudaSuccess) return err;
+        if (occ < 1) occ = 1;
+    }
+    cudaError_t err = cudaMemsetAsync(a.d_counters, 0, sizeof(unsigned long long) * a.n_queries, a.stream);
+    if (err != cudaSuccess) return err;
+    long long want = (a.ps.ntiles + 3) / 4;
+    long long resident = (long long)a.sm_count * occ / (a.n_queries > 0 ? a.n_queries : 1);
+    if (resident < 1) resident = 1;
+    if (want > resident) want = resident;
+    if (want < 1) want = 1;
+    dim3 grid((unsigned)want, (unsigned)a.n_queries);
+    kern<<<grid, THREADS, 0, a.stream>>>(a.ps, static_cast<const BandedRow *>(d_rows_table), a.qlen, e,
+                                         static_cast<int8_t *>(a.d_results), a.result_stride, a.d_counters);
+    return cudaGetLastError();
+}
+cudaError_t launch_banded(const LaunchArgs &a, const void *d_rows_table, int e) {
+    return (2 * e + 2 <= 32) ? launch_banded_t<false>(a, d_rows_table, e) : launch_banded_t<true>(a, d_rows_table, e);
+}
+
+// ---- pack ----------------------------------------------------------------------------------------
+cudaError_t launch_pack(int layout, const void *d_rows, int slen, long long count, void *d_packed, int sm_count,
+                        cudaStream_t stream) {
+    PackedSubjects v = make_packed_view(d_packed, slen, count);
+    if (v.ntiles == 0) return cudaSuccess;
+    long long blocks = (v.ntiles + 3) / 4;
+    const long long cap = (long long)sm_count * 16;
+    if (blocks > cap) blocks = cap;
+    auto codes = const_cast<uint4 *>(v.codes);
+    auto nmask = const_cast<uint32_t *>(v.nmask);
+    auto flags = const_cast<uint8_t *>(v.tile_has_n);
+    if (layout == LAYOUT_CODES)
+        pack_kernel<LAYOUT_CODES><<<(unsigned)blocks, 128, 0, stream>>>(static_cast<const uint8_t *>(d_rows), slen, count,
+                                                                        codes, nmask, flags, v.ntiles, v.ku, v.kn);
+    else
+        pack_kernel<LAYOUT_PLANES><<<(unsigned)blocks, 128, 0, stream>>>(static_cast<const uint8_t *>(d_rows), slen, count,
+                                                                         codes, nmask, flags, v.ntiles, v.ku, v.kn);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_unpeq(int wordbytes, const void *d_peq, int word_num, int usable, int slen, long long count,
+                         int vnum, void *d_packed, int sm_count, cudaStream_t stream) {
+    PackedSubjects v = make_packed_view(d_packed, slen, count);
+    if (v.ntiles == 0) return cudaSuccess;
+    long long blocks = (v.ntiles + 3) / 4;
+    const long long cap = (long long)sm_count * 16;
+    if (blocks > cap) blocks = cap;
+    auto codes = const_cast<uint4 *>(v.codes);
+    auto nmask = const_cast<uint32_t *>(v.nmask);
+    auto flags = const_cast<uint8_t *>(v.tile_has_n);
+    if (wordbytes == 8)
+        unpeq_kernel<uint64_t><<<(unsigned)blocks, 128, 0, stream>>>(static_cast<const uint64_t *>(d_peq), word_num, usable,
+                                                                     slen, count, codes, nmask, flags, v.ntiles, v.ku, v.kn, vnum);
+    else
+        unpeq_kernel<uint32_t><<<(unsigned)blocks, 128, 0, stream>>>(static_cast<const uint32_t *>(d_peq), word_num, usable,
+                                                                     slen, count, codes, nmask, flags, v.ntiles, v.ku, v.kn, vnum);
+    return cudaGetLastError();
+}
+
+// ---- INT32 ALU-pipe probe ----------------------------------------------------------------------
+// 8 independent LOP3 chains per thread, 64 LOP3 per loop trip, 256 threads x 8 CTAs per SM: the
+// ALU pipe (16 lanes per SM sub-partition, LOP3/IADD3/SHF) is the only busy unit.
+__global__ void __launch_bounds__(256) int_peak_kernel(int iters, unsigned int *sink) {
+    uint32_t a0 = threadIdx.x, a1 = a0 * 3u + 1u, a2 = a0 * 5u + 2u, a3 = a0 * 7u + 3u;
+    uint32_t a4 = a0 * 11u + 4u, a5 = a0 * 13u + 5u, a6 = a0 * 17u + 6u, a7 = a0 * 19u + 7u;
+    const uint32_t k1 = blockIdx.x * 0x9e3779b9u + 1u, k2 = ~k1;
+    const long long t0 = clock64();
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+            asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a0) : "r"(k1), "r"(a1));
+            asm volatile("lop3.b32 %0, %0, %1, %2, 0xe8;" : "+r"(a1) : "r"(k2), "r"(a2));
+            asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a2) : "r"(k1), "r"(a3));
+            asm volatile("lop3.b32 %0, %0, %1, %2, 0xe8;" : "+r"(a3) : "r"(k2), "r"(a4));
+            asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a4) : "r"(k1), "r"(a5));
+            asm volatile("lop3.b32 %0, %0, %1, %2, 0xe8;" : "+r"(a5) : "r"(k2), "r"(a6));
+            asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a6) : "r"(k1), "r"(a7));
+            asm volatile("lop3.b32 %0, %0, %1, %2, 0xe8;" : "+r"(a7) : "r"(k2), "r"(a0));
+        }
+    }
+    const uint32_t r = a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7;
+    if (r == 0x12345678u) sink[0] = r;    // practically never true: keeps the chains alive
+    if (blockIdx.x == 0 && threadIdx.x == 0) *reinterpret_cast<long long *>(sink + 2) = clock64() - t0;   // SM cycles
+}
+cudaError_t launch_int_peak(int sm_count, int iters, unsigned int *d_sink, cudaStream_t stream) {
+    int_peak_kernel<<<sm_count * 8, 256, 0, stream>>>(iters, d_sink);
+    return cudaGetLastError();
+}
+
+}  // namespace bgsa

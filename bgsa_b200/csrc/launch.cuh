@@ -1,0 +1,57 @@
+// launch.cuh -- host-side launch helper shared by the instance files.
+#pragma once
+
+#include "align_kernel.cuh"
+
+namespace bgsa {
+
+struct LaunchArgs {
+    PackedSubjects ps;
+    const uint32_t *d_peq;           // [n_queries][5][row stride]
+    int n_queries;
+    int qlen;
+    void *d_results;
+    long long result_stride;
+    unsigned long long *d_counters;  // [n_queries], zeroed by the launcher
+    int sm_count;
+    cudaStream_t stream;
+};
+
+constexpr int kAlignThreads = 128;
+constexpr int kAlignCH = 4;          // 128-bit units (256 bases) per lane and stage
+
+template <class Algo, int L, int UNROLL>
+cudaError_t launch_align(const LaunchArgs &a, typename Algo::Params prm) {
+    auto kern = align_kernel<Algo, L, kAlignCH, kAlignThreads, UNROLL>;
+    static int occ = 0;
+    if (occ == 0) {
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kAlignThreads, 0);
+        if (e != cudaSuccess) return e;
+        if (occ < 1) occ = 1;
+    }
+    cudaError_t e = cudaMemsetAsync(a.d_counters, 0, sizeof(unsigned long long) * a.n_queries, a.stream);
+    if (e != cudaSuccess) return e;
+    const long long warps_per_cta = kAlignThreads / 32;
+    long long want = (a.ps.ntiles + warps_per_cta - 1) / warps_per_cta;       // one tile per warp at least
+    long long resident = (long long)a.sm_count * occ / (a.n_queries > 0 ? a.n_queries : 1);
+    if (resident < 1) resident = 1;
+    if (want > resident) want = resident;
+    if (want < 1) want = 1;
+    dim3 grid((unsigned)want, (unsigned)a.n_queries);
+    kern<<<grid, kAlignThreads, 0, a.stream>>>(a.ps, a.d_peq, a.qlen, static_cast<int16_t *>(a.d_results),
+                                               a.result_stride, prm, a.d_counters);
+    return cudaGetLastError();
+}
+
+// instance-file entry points (return cudaErrorInvalidValue when (K, L) has no instance)
+cudaError_t launch_myers(int mode, int K, int L, const LaunchArgs &a, int sign);
+cudaError_t launch_bitpal_packed(int scheme, int K, int L, const LaunchArgs &a);
+cudaError_t launch_bitpal_nonpacked(int scheme, int K, int L, const LaunchArgs &a);
+cudaError_t launch_banded(const LaunchArgs &a, const void *d_rows_table, int e);
+cudaError_t launch_pack(int layout, const void *d_rows, int slen, long long count, void *d_packed, int sm_count,
+                        cudaStream_t stream);
+cudaError_t launch_unpeq(int wordbytes, const void *d_peq, int word_num, int usable, int slen, long long count,
+                         int vnum, void *d_packed, int sm_count, cudaStream_t stream);
+cudaError_t launch_int_peak(int sm_count, int iters, unsigned int *d_sink, cudaStream_t stream);
+
+}  // namespace bgsa

@@ -1,0 +1,131 @@
+/*
+ * include/bgsa_b200.h -- C ABI of libbgsa_b200.so, the B200 (sm_100a) implementation of BGSA's
+ * one-query-versus-many-subjects alignment hot path.
+ *
+ * Plain C: pointers and sizes only, no CUDA or torch types.  Every entry point returns a
+ * bgsa_status_t (0 = ok); nothing here falls back to the CPU -- if no CUDA device / kernel image
+ * is available the call fails with BGSA_ERR_CUDA.
+ *
+ * What each entry point replaces in the reference (paths relative to sdu-hpcl/BGSA):
+ *
+ *   bgsa_align_batch            original/BGSA_CPU/cal.h:48  cpu_cal_align_score()  (cal_cpu.c:43-85)
+ *                               + original/BGSA_CPU/global.h:24 cpu_handle_reads() (global.c:25-70),
+ *                               and their sse_/avx_/mic_ twins (original/BGSA_AVX512/cal.h:54,
+ *                               global.h:26) and the banded pair (banded/BGSA_CPU/cal.h:48,
+ *                               global.h:24).  One call = one (read bucket x ref bucket x device)
+ *                               iteration of cal_on_cpu() (cal_cpu.c:363-401) / mic_cal()
+ *                               (original/BGSA_KNC/cal_mic.c:86-153).
+ *   bgsa_pack_subjects_device   global.c:25-70 (Peq build) -- replaced by a 2-bit pack + transpose.
+ *   bgsa_align_device           the generated kernels align_cpu/align_sse/align_avx/align_mic
+ *                               (original/BGSA_CPU/align_core.h:8 and twins), batched.
+ *   align_core.h (this dir)     the per-chunk kernel symbols themselves, for unmodified callers.
+ */
+#ifndef BGSA_B200_H
+#define BGSA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum bgsa_status_t {
+    BGSA_OK = 0,
+    BGSA_ERR_ARG = 1,         /* null pointer, non-positive length, negative count ...            */
+    BGSA_ERR_UNSUPPORTED = 2, /* scoring scheme / length / threshold has no kernel instance       */
+    BGSA_ERR_CUDA = 3,        /* CUDA runtime error (message: bgsa_last_error())                  */
+    BGSA_ERR_NOMEM = 4
+} bgsa_status_t;
+
+/* Algorithms on the path.  The numeric values are part of the ABI. */
+typedef enum bgsa_algo_t {
+    BGSA_MYERS_GLOBAL = 0,     /* generator -m, original/BGSA_CPU/align_core.c                    */
+    BGSA_MYERS_SEMIGLOBAL = 1, /* generator -m -s, MyersGenerator.java:56-223                     */
+    BGSA_BANDED_MYERS = 2,     /* generator -b, banded/BGSA_CPU/align_core.c, result int8         */
+    BGSA_BITPAL_PACKED = 3,    /* generator -M -I -G, original/BGSA_AVX512/align_core.c           */
+    BGSA_BITPAL_NONPACKED = 4  /* generator -t non-packed, BitPAlGenerator.java:1392-1701         */
+} bgsa_algo_t;
+
+/* What the reference bakes into the generated align_core.c (align_core.c:13-17) plus -k. */
+typedef struct bgsa_params_t {
+    int32_t algo;        /* bgsa_algo_t                                                          */
+    int32_t match;       /* BitPAl only (Myers/banded force 0,-1,-1: Main.java:253-257)          */
+    int32_t mismatch;
+    int32_t gap;
+    int32_t threshold;   /* banded only: -k, default 31 (banded/BGSA_CPU/main.c:43)              */
+    int32_t myers_sign;  /* Myers only: -1 => score = -distance (generator -m 0, the checked-in
+                            kernels), +1 => +distance (-m 1, Main.java:127-141).  0 means -1.    */
+} bgsa_params_t;
+
+/* seq_t, bit-for-bit (original/BGSA_CPU/global.h:9-16). */
+typedef struct bgsa_seq_t {
+    int32_t len;
+    int64_t size;
+    int64_t count;
+    int32_t extra_size;
+    int32_t extra_count;
+    char *content;       /* ASCII rows of stride len+1 (the '\n' is kept)                        */
+} bgsa_seq_t;
+
+/* ---- library / device ------------------------------------------------------------------ */
+const char *bgsa_version(void);
+const char *bgsa_last_error(void);                  /* thread-local, never NULL                  */
+int bgsa_device_count(int *count);
+void bgsa_params_default(bgsa_params_t *p, int algo); /* 2/-3/-5, threshold 31, sign -1          */
+/* bytes per score: 1 for BGSA_BANDED_MYERS (common_write_t int8_t, banded/BGSA_CPU/config.h:21),
+ * else 2 (int16_t, original/BGSA_CPU/config.h:19). */
+int bgsa_result_size(int algo);
+/* BGSA_OK iff (params, query_len, subject_len) has a kernel instance. */
+int bgsa_supported(const bgsa_params_t *p, int query_len, int subject_len);
+
+/* ---- host-buffer batch entry (the reference-facing call) ------------------------------- *
+ * queries : code rows 0..4 of stride query_len+1, exactly what get_ref_from_file() leaves in
+ *           ref_seq.content (file.c:117-140).
+ * subjects: bgsa_seq_t with ASCII rows; subjects [first, first+count) are aligned.
+ * results : [query][subject] row-major (cal_cpu.c:79-82), element (qi, si) at
+ *           results[qi * result_stride + si], int16_t or int8_t (bgsa_result_size).
+ * device  : CUDA ordinal.  Blocking; host<->device copies are inside the call.
+ */
+int bgsa_align_batch(const bgsa_params_t *p, const char *queries, int n_queries, int query_len,
+                     const bgsa_seq_t *subjects, int64_t first, int64_t count,
+                     void *results, int64_t result_stride, int device);
+
+/* Asynchronous pair for double-buffered pipelines (thread.c:35-170 ping-pong): submit returns
+ * as soon as the work is queued on the device's stream `slot` (0 or 1); wait blocks until the
+ * results of that slot are in `results`.  Host buffers must stay valid until wait returns. */
+int bgsa_align_batch_submit(const bgsa_params_t *p, const char *queries, int n_queries, int query_len,
+                            const bgsa_seq_t *subjects, int64_t first, int64_t count,
+                            void *results, int64_t result_stride, int device, int slot);
+int bgsa_align_batch_wait(int device, int slot);
+/* Pinned host memory for the buffers above (malloc_mem/free_mem, global.c:17-23). */
+void *bgsa_malloc_host(size_t bytes);
+void bgsa_free_host(void *p);
+
+/* ---- device-resident entries (inputs already in HBM; used for kernel-only timing) ------ */
+/* Size in bytes of the packed form of `count` subjects of `subject_len` bases. */
+int64_t bgsa_packed_bytes(int subject_len, int64_t count);
+/* d_rows: device pointer to ASCII rows (stride subject_len+1); d_packed: device buffer of
+ * bgsa_packed_bytes().  p->algo selects the encoding the kernel of that algorithm consumes
+ * (2-bit codes, or two bit-planes for BGSA_BANDED_MYERS).  stream: a cudaStream_t cast to
+ * void* (NULL = default stream). */
+int bgsa_pack_subjects_device(const bgsa_params_t *p, const void *d_rows, int subject_len, int64_t count,
+                              void *d_packed, int device, void *stream);
+/* h_queries: host code rows as above; d_results: device [query][count] scores. */
+int bgsa_align_device(const bgsa_params_t *p, const char *h_queries, int n_queries, int query_len,
+                      const void *d_packed, int subject_len, int64_t count,
+                      void *d_results, int64_t result_stride, int device, void *stream);
+/* Number of kernel launches issued by this library since load (bench.py "gpu_launches"). */
+int64_t bgsa_launch_count(void);
+/* Name of the kernel instance bgsa_align_device would use, e.g. "bitpal_packed<2,-3,-5,K=5,L=1>". */
+int bgsa_kernel_name(const bgsa_params_t *p, int query_len, int subject_len, char *buf, int buflen);
+
+/* ---- integer-pipe roofline probe ---------------------------------------------------------
+ * Runs a LOP3/IADD3 throughput microbenchmark on `device` and reports lane-operations per
+ * second on the INT32 ALU pipe (MEASURED_PEAKS.json has no integer figure). */
+int bgsa_int_peak(int device, double *lane_ops_per_s, double *sm_clock_mhz);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BGSA_B200_H */
