@@ -68,16 +68,18 @@ align_kernel(PackedSubjects ps, const uint32_t *__restrict__ g_peq, int qlen, in
     const int slen = ps.slen, ku = ps.ku;
     const int nstages = (ku + CH - 1) / CH;
 
-    long long tile = next_tile(counter, lane);
+    // work unit = (tile, pass): the 32/L subjects of a tile that a warp has in flight at once
+    const long long nunits = ps.ntiles * L;
+    long long unit = next_tile(counter, lane);
     int sb = 0;
-    if (tile < ps.ntiles) st.issue(0, ps.codes + tile * ku * 32, min(CH, ku), lane);
+    if (unit < nunits) st.issue(0, ps.codes + (unit / L) * ku * 32, min(CH, ku), lane);
 
-    while (tile < ps.ntiles) {
+    while (unit < nunits) {
         const long long nxt = next_tile(counter, lane);
+        const long long tile = unit / L;
+        const int pass = (int)(unit % L);
         const bool with_n = ps.tile_has_n[tile] != 0;
-
-#pragma unroll 1
-        for (int pass = 0; pass < L; pass++) {
+        {
             const int sidx = pass * GROUPS + group;          // subject of this group inside the tile
             typename Algo::State state;
             Algo::init(state);
@@ -98,13 +100,11 @@ align_kernel(PackedSubjects ps, const uint32_t *__restrict__ g_peq, int qlen, in
             };
 
             for (int sg = 0; sg < nstages; sg++) {
-                // prefetch the following stage (same tile & pass, next pass, or next tile)
+                // prefetch the following stage (same unit, or the first stage of the next unit)
                 if (sg + 1 < nstages)
                     st.issue(sb ^ 1, ps.codes + (tile * ku + (long long)(sg + 1) * CH) * 32, min(CH, ku - (sg + 1) * CH), lane);
-                else if (pass + 1 < L)
-                    st.issue(sb ^ 1, ps.codes + tile * ku * 32, min(CH, ku), lane);
-                else if (nxt < ps.ntiles)
-                    st.issue(sb ^ 1, ps.codes + nxt * ku * 32, min(CH, ku), lane);
+                else if (nxt < nunits)
+                    st.issue(sb ^ 1, ps.codes + (nxt / L) * ku * 32, min(CH, ku), lane);
                 st.wait(sb);
                 const int units = min(CH, ku - sg * CH);
                 for (int u = 0; u < units; u++) {
@@ -165,7 +165,7 @@ align_kernel(PackedSubjects ps, const uint32_t *__restrict__ g_peq, int qlen, in
             const long long subject = tile * kTileSubjects + sidx;
             if (rank == 0 && subject < ps.count) out[subject] = narrow16(Algo::final_score(total, best, qlen, slen, prm));
         }
-        tile = nxt;
+        unit = nxt;
     }
 }
 

@@ -133,21 +133,31 @@ struct Buf {
 };
 struct QueryCache {          // device copy of the query-side tables of the last call
     Buf d_tab;               // Peq rows, or BandedRow table
-    Buf d_counters;
     std::vector<char> key;   // (plan, queries) it was built from
     void *pinned = nullptr;
     size_t pinned_cap = 0;
 };
-struct Slot {
+// One in-flight chunk: its own stream and device buffers, so that the H2D copy of chunk i+1
+// overlaps the kernels of chunk i and the D2H copy of chunk i-1 (three different engines).
+struct Lane {
     cudaStream_t stream = nullptr;
-    Buf d_rows, d_packed, d_results;
+    Buf d_rows, d_packed, d_results, d_counters;
+};
+constexpr int kLanesPerJob = 3;
+// A "job" = one bgsa_align_batch_submit() call: the subject range is cut into chunks that
+// rotate over the job's lanes.  Two jobs (slot 0 / 1) can be in flight per device, mirroring the
+// reference's a/b ping-pong buffers (cal_cpu.c:258-267, thread.c:35-170).
+struct Job {
+    Lane lane[kLanesPerJob];
     QueryCache qc;
+    cudaEvent_t tab_ready = nullptr;
 };
 struct DeviceCtx {
     bool ready = false;
     int sm_count = 0;
-    Slot slot[2];
+    Job job[2];
     QueryCache resident_qc;  // bgsa_align_device (caller's stream)
+    Buf resident_counters;
 };
 constexpr int kMaxDevices = 64;
 DeviceCtx g_ctx[kMaxDevices];
@@ -160,7 +170,10 @@ int get_ctx(int device, DeviceCtx **out) {
     DeviceCtx &c = g_ctx[device];
     if (!c.ready) {
         CUDA_TRY(cudaDeviceGetAttribute(&c.sm_count, cudaDevAttrMultiProcessorCount, device));
-        for (Slot &s : c.slot) CUDA_TRY(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+        for (Job &j : c.job) {
+            for (Lane &l : j.lane) CUDA_TRY(cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking));
+            CUDA_TRY(cudaEventCreateWithFlags(&j.tab_ready, cudaEventDisableTiming));
+        }
         c.ready = true;
     }
     *out = &c;
@@ -169,16 +182,14 @@ int get_ctx(int device, DeviceCtx **out) {
 
 // Build (or reuse) the query-side tables on the device.  Returns the device pointer in *d_tab.
 int stage_queries(QueryCache &qc, const Plan &plan, const char *queries, int nq, int qlen, int slen, cudaStream_t stream,
-                  const void **d_tab, unsigned long long **d_counters) {
+                  const void **d_tab) {
     const size_t qbytes = (size_t)nq * (qlen + 1);
     std::vector<char> key(sizeof(Plan) + sizeof(int) * 3 + qbytes);
     memcpy(key.data(), &plan, sizeof(Plan));
     const int dims[3] = {nq, qlen, slen};
     memcpy(key.data() + sizeof(Plan), dims, sizeof(dims));
     memcpy(key.data() + sizeof(Plan) + sizeof(dims), queries, qbytes);
-    int rc = qc.d_counters.ensure(sizeof(unsigned long long) * (size_t)nq);
-    if (rc) return rc;
-    *d_counters = static_cast<unsigned long long *>(qc.d_counters.p);
+    int rc;
     if (key == qc.key && qc.d_tab.p) { *d_tab = qc.d_tab.p; return BGSA_OK; }
 
     size_t bytes;
@@ -324,11 +335,12 @@ int bgsa_align_device(const bgsa_params_t *p, const char *h_queries, int n_queri
     if (rc) return rc;
     if (count == 0 || n_queries == 0) return BGSA_OK;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const void *d_tab; unsigned long long *d_counters;
-    rc = stage_queries(ctx->resident_qc, plan, h_queries, n_queries, query_len, subject_len, st, &d_tab, &d_counters);
+    const void *d_tab;
+    rc = stage_queries(ctx->resident_qc, plan, h_queries, n_queries, query_len, subject_len, st, &d_tab);
     if (rc) return rc;
-    return run_align(plan, ctx->sm_count, d_tab, d_counters, n_queries, query_len, d_packed, subject_len, count, d_results,
-                     result_stride, st);
+    if ((rc = ctx->resident_counters.ensure(sizeof(unsigned long long) * (size_t)n_queries))) return rc;
+    return run_align(plan, ctx->sm_count, d_tab, static_cast<unsigned long long *>(ctx->resident_counters.p), n_queries,
+                     query_len, d_packed, subject_len, count, d_results, result_stride, st);
 }
 
 int bgsa_align_batch_submit(const bgsa_params_t *p, const char *queries, int n_queries, int query_len,
@@ -346,26 +358,41 @@ int bgsa_align_batch_submit(const bgsa_params_t *p, const char *queries, int n_q
     rc = get_ctx(device, &ctx);
     if (rc) return rc;
     if (count == 0 || n_queries == 0) return BGSA_OK;
-    Slot &s = ctx->slot[slot];
+    Job &job = ctx->job[slot];
     const int slen = subjects->len;
-    const size_t row_bytes = (size_t)count * (slen + 1);
     const size_t esize = plan.result_size;
-    if ((rc = s.d_rows.ensure(row_bytes + 16))) return rc;
-    if ((rc = s.d_packed.ensure((size_t)packed_bytes(slen, count)))) return rc;
-    if ((rc = s.d_results.ensure(esize * (size_t)n_queries * (size_t)count))) return rc;
-    // host -> device: the ASCII rows exactly as file.c:44-115 left them
-    CUDA_TRY(cudaMemcpyAsync(s.d_rows.p, subjects->content + (size_t)first * (slen + 1), row_bytes, cudaMemcpyHostToDevice, s.stream));
-    cudaError_t e = launch_pack(plan.layout, s.d_rows.p, slen, count, s.d_packed.p, ctx->sm_count, s.stream);
-    if (e != cudaSuccess) return fail(BGSA_ERR_CUDA, "pack kernel launch failed: %s", cudaGetErrorString(e));
-    g_launches.fetch_add(1);
-    const void *d_tab; unsigned long long *d_counters;
-    rc = stage_queries(s.qc, plan, queries, n_queries, query_len, slen, s.stream, &d_tab, &d_counters);
+    // query-side tables once per job, on lane 0's stream; the other lanes wait on the event
+    const void *d_tab;
+    rc = stage_queries(job.qc, plan, queries, n_queries, query_len, slen, job.lane[0].stream, &d_tab);
     if (rc) return rc;
-    rc = run_align(plan, ctx->sm_count, d_tab, d_counters, n_queries, query_len, s.d_packed.p, slen, count, s.d_results.p, count, s.stream);
-    if (rc) return rc;
-    // device -> host: [query][subject] rows into the caller's (possibly wider) result matrix
-    CUDA_TRY(cudaMemcpy2DAsync(results, esize * (size_t)result_stride, s.d_results.p, esize * (size_t)count, esize * (size_t)count,
-                               (size_t)n_queries, cudaMemcpyDeviceToHost, s.stream));
+    CUDA_TRY(cudaEventRecord(job.tab_ready, job.lane[0].stream));
+    // chunking: tile-aligned, at most ~8 chunks, never below 32 Ki subjects (launch overheads)
+    int64_t chunk = (count + 7) / 8;
+    if (chunk < 32768) chunk = 32768;
+    chunk = (chunk + kTileSubjects - 1) / kTileSubjects * kTileSubjects;
+    int li = 0;
+    for (int64_t off = 0; off < count; off += chunk, li = (li + 1) % kLanesPerJob) {
+        const int64_t n = count - off < chunk ? count - off : chunk;
+        Lane &l = job.lane[li];
+        const size_t row_bytes = (size_t)n * (slen + 1);
+        if ((rc = l.d_rows.ensure(row_bytes + 16))) return rc;
+        if ((rc = l.d_packed.ensure((size_t)packed_bytes(slen, n)))) return rc;
+        if ((rc = l.d_results.ensure(esize * (size_t)n_queries * (size_t)n))) return rc;
+        if ((rc = l.d_counters.ensure(sizeof(unsigned long long) * (size_t)n_queries))) return rc;
+        // host -> device: the ASCII rows exactly as file.c:44-115 left them
+        CUDA_TRY(cudaMemcpyAsync(l.d_rows.p, subjects->content + (size_t)(first + off) * (slen + 1), row_bytes,
+                                 cudaMemcpyHostToDevice, l.stream));
+        cudaError_t e = launch_pack(plan.layout, l.d_rows.p, slen, n, l.d_packed.p, ctx->sm_count, l.stream);
+        if (e != cudaSuccess) return fail(BGSA_ERR_CUDA, "pack kernel launch failed: %s", cudaGetErrorString(e));
+        g_launches.fetch_add(1);
+        if (li != 0) CUDA_TRY(cudaStreamWaitEvent(l.stream, job.tab_ready, 0));
+        rc = run_align(plan, ctx->sm_count, d_tab, static_cast<unsigned long long *>(l.d_counters.p), n_queries, query_len,
+                       l.d_packed.p, slen, n, l.d_results.p, n, l.stream);
+        if (rc) return rc;
+        // device -> host: [query][subject] rows into the caller's (possibly wider) result matrix
+        CUDA_TRY(cudaMemcpy2DAsync(static_cast<char *>(results) + esize * (size_t)off, esize * (size_t)result_stride, l.d_results.p,
+                                   esize * (size_t)n, esize * (size_t)n, (size_t)n_queries, cudaMemcpyDeviceToHost, l.stream));
+    }
     return BGSA_OK;
 }
 
@@ -374,7 +401,7 @@ int bgsa_align_batch_wait(int device, int slot) {
     DeviceCtx *ctx;
     int rc = get_ctx(device, &ctx);
     if (rc) return rc;
-    CUDA_TRY(cudaStreamSynchronize(ctx->slot[slot].stream));
+    for (Lane &l : ctx->job[slot].lane) CUDA_TRY(cudaStreamSynchronize(l.stream));
     return BGSA_OK;
 }
 
@@ -396,10 +423,12 @@ int bgsa_int_peak(int device, double *lane_ops_per_s, double *sm_clock_mhz) {
     cudaEvent_t e0, e1;
     CUDA_TRY(cudaEventCreate(&e0));
     CUDA_TRY(cudaEventCreate(&e1));
-    cudaStream_t st = ctx->slot[0].stream;
+    cudaStream_t st = ctx->job[0].lane[0].stream;
     const int iters = 20000;
     double best = 0.0, best_mhz = 0.0;
     for (int rep = 0; rep < 4; rep++) {           // rep 0 = warm-up
+        const long long init[2] = {0x7fffffffffffffffLL, 0LL};
+        CUDA_TRY(cudaMemcpyAsync(d_sink + 2, init, sizeof(init), cudaMemcpyHostToDevice, st));
         CUDA_TRY(cudaEventRecord(e0, st));
         cudaError_t e = launch_int_peak(ctx->sm_count, iters, d_sink, st);
         if (e != cudaSuccess) return fail(BGSA_ERR_CUDA, "int_peak launch failed: %s", cudaGetErrorString(e));
@@ -408,8 +437,9 @@ int bgsa_int_peak(int device, double *lane_ops_per_s, double *sm_clock_mhz) {
         CUDA_TRY(cudaEventSynchronize(e1));
         float ms = 0.f;
         CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
-        long long cycles = 0;
-        CUDA_TRY(cudaMemcpy(&cycles, d_sink + 2, sizeof(cycles), cudaMemcpyDeviceToHost));
+        long long span[2] = {0, 0};
+        CUDA_TRY(cudaMemcpy(span, d_sink + 2, sizeof(span), cudaMemcpyDeviceToHost));
+        const long long cycles = span[1] - span[0];
         const double ops = (double)ctx->sm_count * 8 * 256 * (double)iters * 64.0;
         const double rate = ops / (ms * 1e-3);
         if (rep > 0 && rate > best) { best = rate; best_mhz = (double)cycles / (ms * 1e3); }

@@ -121,7 +121,13 @@ __global__ void __launch_bounds__(256) int_peak_kernel(int iters, unsigned int *
     }
     const uint32_t r = a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7;
     if (r == 0x12345678u) sink[0] = r;    // practically never true: keeps the chains alive
-    if (blockIdx.x == 0 && threadIdx.x == 0) *reinterpret_cast<long long *>(sink + 2) = clock64() - t0;   // SM cycles
+    // SM clock: span of clock64() over the CTAs that ran on SM 0 (clock64 is a per-SM counter)
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    if (threadIdx.x == 0 && smid == 0) {
+        atomicMin(reinterpret_cast<long long *>(sink + 2), t0);
+        atomicMax(reinterpret_cast<long long *>(sink + 4), (long long)clock64());
+    }
 }
 cudaError_t launch_int_peak(int sm_count, int iters, unsigned int *d_sink, cudaStream_t stream) {
     int_peak_kernel<<<sm_count * 8, 256, 0, stream>>>(iters, d_sink);

@@ -1,0 +1,251 @@
+"""GPU tier (-m gpu): the CUDA path, called through the C ABI (bgsa_b200 ctypes binding of
+include/bgsa_b200.h), must be bit-identical to the oracle / the reference vectors.  Nothing here
+reads /root/reference.  Integer results: the bar is exact equality everywhere."""
+import numpy as np
+import pytest
+
+import refutil as R
+import synth
+
+pytestmark = pytest.mark.gpu
+
+ORACLE_ALGO = {0: R.ALGO_MYERS_GLOBAL, 1: R.ALGO_MYERS_SEMIGLOBAL, 2: R.ALGO_BANDED, 3: R.ALGO_BITPAL_PACKED,
+               4: R.ALGO_BITPAL_PACKED}
+
+
+@pytest.fixture(scope="module")
+def B():
+    import torch
+    assert torch.cuda.is_available(), "GPU tier needs a CUDA device"
+    import bgsa_b200 as B
+    B.load()
+    return B
+
+
+@pytest.fixture(scope="module")
+def vec(golden_dir):
+    return np.load(golden_dir / "ref_vectors.npz")
+
+
+def gpu(B, algo, q, s, **kw):
+    before = B.launch_count()
+    out = B.align_batch(B.Params.default(algo, **kw), q, s)
+    assert B.launch_count() > before or s.shape[0] == 0     # our kernels really ran
+    return out
+
+
+def expect(algo, q, s, **kw):
+    return R.oracle_batch(ORACLE_ALGO[algo], q, s, M=kw.get("match", 2), I=kw.get("mismatch", -3), G=kw.get("gap", -5),
+                          e=kw.get("threshold", 5))
+
+
+# ---- C1: the reference's own fixture, and its only checked-in golden ------------------------------
+def test_c1_sample_data_md5(B, vec):
+    import hashlib
+    q, s = R.sample_data()
+    got = gpu(B, B.MYERS_GLOBAL, q, s)
+    assert hashlib.md5(got.tobytes()).hexdigest() == "7253c1f2a6423aaa3e29577acc137302"   # original/BGSA_CPU result.bin
+    assert (got == vec["sample_myers_cpu"]).all()
+    bp = gpu(B, B.BITPAL_PACKED, q, s)
+    assert (bp == vec["sample_bitpal_avx512"]).all()
+    assert (gpu(B, B.BITPAL_NONPACKED, q, s) == bp).all()
+    assert (gpu(B, B.BANDED_MYERS, q, s, threshold=31) == vec["sample_banded_k31"]).all()
+
+
+def test_semiglobal_checked_in_golden(B, golden_dir):
+    g = np.load(golden_dir / "golden_semiglobal_knc.npz")
+    q, s = R.sample_data()
+    assert (gpu(B, B.MYERS_SEMIGLOBAL, q, s) == g["scores"]).all()
+
+
+# ---- slices of C2..C5 against vectors produced by the unmodified reference ------------------------
+@pytest.mark.parametrize("name,algo,key,kw", [
+    ("C2", 3, "C2_ref", {}), ("C2", 4, "C2_ref", {}), ("C2", 0, "C2_myers_ref", {}),
+    ("C3", 2, "C3_ref", {"threshold": 5}),
+    ("C4", 1, "C4_ref_restated", {}), ("C4", 0, "C4_myers_ref", {}),
+    ("C5", 3, "C5_ref", {}),
+])
+def test_config_slices_vs_reference_vectors(B, vec, name, algo, key, kw):
+    got = gpu(B, algo, vec[f"{name}_query"], vec[f"{name}_subjects"], **kw)
+    assert (got == vec[key]).all()
+
+
+@pytest.mark.parametrize("i", range(5))
+def test_ragged_and_n_vs_reference_vectors(B, vec, i):
+    q, s = vec[f"rag{i}_query"], vec[f"rag{i}_subjects"]
+    assert (gpu(B, B.MYERS_GLOBAL, q, s) == vec[f"rag{i}_myers"]).all()
+    assert (gpu(B, B.BITPAL_PACKED, q, s) == vec[f"rag{i}_bitpal"]).all()
+    assert (gpu(B, B.BITPAL_NONPACKED, q, s) == vec[f"rag{i}_bitpal"]).all()
+
+
+# ---- every kernel geometry (K, L) against the oracle ----------------------------------------------
+LENGTHS = [(1, 1, 3), (31, 40, 33), (32, 32, 64), (33, 20, 65), (96, 100, 130), (150, 150, 700), (160, 150, 97),
+           (161, 300, 60), (256, 256, 100), (500, 480, 200), (640, 100, 70), (1000, 1000, 90), (1024, 64, 40),
+           (1025, 200, 40), (2048, 300, 36), (2100, 500, 35), (4100, 300, 33), (5000, 700, 33), (8192, 64, 33)]
+
+
+@pytest.mark.parametrize("ql,sl,ns", LENGTHS)
+def test_all_geometries_vs_oracle(B, ql, sl, ns):
+    rng = np.random.default_rng(ql * 131 + sl)
+    q = R.random_rows(rng, 2, ql, with_n=0.01)
+    s = R.random_rows(rng, ns, sl, with_n=0.01)
+    s[: ns // 3, : min(ql, sl)] = q[0, : min(ql, sl)]
+    for algo in (B.MYERS_GLOBAL, B.MYERS_SEMIGLOBAL, B.BITPAL_PACKED):
+        assert (gpu(B, algo, q, s) == expect(algo, q, s)).all(), (algo, ql, sl)
+    if ql <= 5120:
+        assert (gpu(B, B.BITPAL_NONPACKED, q, s) == expect(3, q, s)).all()
+    for M, I, G in ((1, -1, -1), (1, -3, -2)):
+        kw = dict(match=M, mismatch=I, gap=G)
+        assert (gpu(B, B.BITPAL_PACKED, q, s, **kw) == expect(3, q, s, **kw)).all(), (M, I, G, ql, sl)
+    if ql <= 2048:
+        kw = dict(match=1, mismatch=-3, gap=-2)
+        assert (gpu(B, B.BITPAL_NONPACKED, q, s, **kw) == expect(3, q, s, **kw)).all()
+
+
+def test_myers_long_queries(B):
+    rng = np.random.default_rng(3)
+    for ql, sl in ((16384, 300), (20000, 150), (32768, 100)):
+        q = R.random_rows(rng, 1, ql); s = R.random_rows(rng, 33, sl)
+        s[0, :sl] = q[0, 5000:5000 + sl]
+        for algo in (B.MYERS_GLOBAL, B.MYERS_SEMIGLOBAL):
+            assert (gpu(B, algo, q, s) == expect(algo, q, s)).all(), (algo, ql, sl)
+
+
+@pytest.mark.parametrize("L,e", [(100, 5), (100, 15), (100, 16), (100, 31), (64, 3), (50, 5), (33, 1), (250, 7), (640, 20), (333, 31), (1000, 10)])
+def test_banded_vs_oracle(B, L, e):
+    rng = np.random.default_rng(L * 37 + e)
+    q = R.random_rows(rng, 2, L, with_n=0.005)
+    s = np.concatenate([R.mutate_rows(rng, q[0, :L], 300, 2 * e + 2), R.indel_rows(rng, q[1, :L], 200, e + 3),
+                        R.random_rows(rng, 77, L, with_n=0.01)])
+    got = gpu(B, B.BANDED_MYERS, q, s, threshold=e)
+    exp = expect(2, q, s, threshold=e)
+    assert (got == exp).all()
+    assert (exp == 127).any() and (exp < 127).any()
+
+
+# ---- edge cases ------------------------------------------------------------------------------------
+def test_empty_and_tiny_batches(B):
+    rng = np.random.default_rng(1)
+    q = R.random_rows(rng, 1, 150)
+    empty = np.zeros((0, 151), np.uint8)
+    assert gpu(B, B.BITPAL_PACKED, q, empty).shape == (1, 0)
+    for ns in (1, 31, 32, 33):
+        s = R.random_rows(rng, ns, 150)
+        assert (gpu(B, B.BITPAL_PACKED, q, s) == expect(3, q, s)).all()
+
+
+def test_subrange_and_result_stride(B):
+    rng = np.random.default_rng(2)
+    q = R.random_rows(rng, 3, 150); s = R.random_rows(rng, 500, 150)
+    p = B.Params.default(B.MYERS_GLOBAL)
+    out = np.full((3, 640), 7, np.int16)
+    B.align_batch(p, q, s, first=100, count=333, out=out[:, 64:64 + 333])
+    exp = expect(0, q, s[100:433])
+    assert (out[:, 64:64 + 333] == exp).all() and (out[:, :64] == 7).all() and (out[:, 397:] == 7).all()
+
+
+def test_non_acgtn_bytes_behave_as_A(B):
+    # Appendix A3: mapping_table is zero-initialised, so any other byte is 'A'
+    rng = np.random.default_rng(4)
+    q = R.random_rows(rng, 1, 100); s = R.random_rows(rng, 64, 100)
+    s2 = s.copy(); s2[s2 == ord("A")] = ord("x"); s2[5, 7] = ord("a"); s2[6, 8] = ord("-")
+    s_ref = s.copy(); s_ref[5, 7] = ord("A"); s_ref[6, 8] = ord("A")
+    for algo in (B.MYERS_GLOBAL, B.BITPAL_PACKED):
+        assert (gpu(B, algo, q, s2) == gpu(B, algo, q, s_ref)).all()
+    assert (gpu(B, B.BANDED_MYERS, q, s2, threshold=9) == gpu(B, B.BANDED_MYERS, q, s_ref, threshold=9)).all()
+
+
+def test_int16_wrap_like_reference(B):
+    L = 6000
+    q = np.full((1, L + 1), ord("A"), np.uint8); q[:, L] = 10
+    s = np.full((40, L + 1), ord("C"), np.uint8); s[:, L] = 10
+    s[1, :L] = ord("A")
+    got = gpu(B, B.MYERS_GLOBAL, q, s)
+    assert got[0, 0] == -6000 and got[0, 1] == 0
+    # (2,-3,-5) on 6 kbp of pure mismatches: -18000 fits; the narrowing itself is covered by 8 kbp of gaps below
+    bp = gpu(B, B.BITPAL_PACKED, q, s)
+    assert bp[0, 0] == -18000 and bp[0, 1] == 12000
+    q2 = np.full((1, 8001), ord("A"), np.uint8); q2[:, 8000] = 10
+    s3 = np.full((33, 11), ord("C"), np.uint8); s3[:, 10] = 10
+    bp2 = gpu(B, B.BITPAL_PACKED, q2, s3)          # true score -5*7990 - 3*10 = -39980 -> wraps
+    assert bp2[0, 0] == np.int16(np.int32(-39980).astype(np.int16)) and (bp2 == expect(3, q2, s3)).all()
+
+
+def test_many_queries_layout(B):
+    # [query][subject] row-major (cal_cpu.c:79-82), more queries than one ref bucket (REF_BUCKET_COUNT 100)
+    rng = np.random.default_rng(5)
+    q = R.random_rows(rng, 130, 90); s = R.random_rows(rng, 70, 100)
+    for algo in (B.MYERS_GLOBAL, B.BITPAL_PACKED):
+        assert (gpu(B, algo, q, s) == expect(algo, q, s)).all()
+
+
+# ---- full-size runs: size-independent properties + oracle on a sample ------------------------------
+def _sample_check(B, algo, q, s, got, rng, n=512, **kw):
+    idx = np.sort(rng.choice(s.shape[0], size=n, replace=False))
+    assert (got[:, idx] == expect(algo, q, np.ascontiguousarray(s[idx]), **kw)).all()
+
+
+def test_c2_full_size_properties(B):
+    q, s = synth.make("C2")
+    assert s.shape == (1_000_000, 151)
+    got = gpu(B, B.BITPAL_PACKED, q, s)
+    rng = np.random.default_rng(0)
+    _sample_check(B, 3, q, s, got, rng)
+    # permutation equivariance: scoring a shuffled database gives the shuffled scores
+    perm = rng.permutation(s.shape[0])
+    assert (gpu(B, B.BITPAL_PACKED, q, np.ascontiguousarray(s[perm])) == got[:, perm]).all()
+    # symmetry of the global score: swap the roles of query and subject for a few pairs
+    for i in (0, 1, 999_999):
+        qi = np.ascontiguousarray(s[i:i + 1]); si = np.ascontiguousarray(q)
+        assert gpu(B, B.BITPAL_PACKED, qi, si)[0, 0] == got[0, i]
+    # self alignment = match * length; Myers distance of the query to itself = 0
+    assert gpu(B, B.BITPAL_PACKED, q, q)[0, 0] == 2 * 150
+    assert gpu(B, B.MYERS_GLOBAL, q, q)[0, 0] == 0
+    # a checksum of the whole score vector recomputed from two halves (sub-range API)
+    p = B.Params.default(B.BITPAL_PACKED)
+    a = B.align_batch(p, q, s, first=0, count=400_007)
+    b = B.align_batch(p, q, s, first=400_007, count=599_993)
+    assert int(a.astype(np.int64).sum() + b.astype(np.int64).sum()) == int(got.astype(np.int64).sum())
+
+
+def test_c3_full_size_properties(B):
+    q, s = synth.make("C3", 2_000_000)
+    got = gpu(B, B.BANDED_MYERS, q, s, threshold=5)
+    rng = np.random.default_rng(1)
+    _sample_check(B, 2, q, s, got, rng, n=2048, threshold=5)
+    frac_ok = (got[0, : s.shape[0] // 2] < 127).mean()
+    assert 0.5 < frac_ok < 1.0                       # the similar half mostly verifies ...
+    assert (got[0, s.shape[0] // 2:] == 127).mean() > 0.999    # ... the random half is rejected
+    assert got.min() >= 0
+
+
+def test_c4_slice_properties(B):
+    q, s = synth.make("C4", 20_000)
+    got = gpu(B, B.MYERS_SEMIGLOBAL, q, s)
+    glob = gpu(B, B.MYERS_GLOBAL, q, s)
+    rng = np.random.default_rng(2)
+    _sample_check(B, 1, q, s, got, rng, n=96)
+    assert (got >= glob).all()                       # -distance: a free query substring can only help
+    assert gpu(B, B.MYERS_SEMIGLOBAL, q, np.ascontiguousarray(q))[0, 0] == 0
+
+
+def test_c5_slice(B):
+    q, s = synth.make("C5", 300)
+    got = gpu(B, B.BITPAL_PACKED, q, s)
+    rng = np.random.default_rng(3)
+    _sample_check(B, 3, q, s, got, rng, n=24)
+    assert gpu(B, B.BITPAL_PACKED, q, q)[0, 0] == 10000
+
+
+def test_device_resident_api_matches_host_api(B):
+    import torch
+    q, s = synth.make("C2", 50_000)
+    p = B.Params.default(B.BITPAL_PACKED)
+    d_rows = torch.from_numpy(s.reshape(-1)).cuda()
+    d_packed = torch.empty(B.packed_bytes(150, s.shape[0]), dtype=torch.uint8, device="cuda")
+    d_res = torch.empty(s.shape[0], dtype=torch.int16, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    B.pack_subjects_device(p, d_rows.data_ptr(), 150, s.shape[0], d_packed.data_ptr(), 0, st)
+    B.align_device(p, q, d_packed.data_ptr(), 150, s.shape[0], d_res.data_ptr(), s.shape[0], 0, st)
+    torch.cuda.synchronize()
+    assert (d_res.cpu().numpy()[None, :] == B.align_batch(p, q, s)).all()

@@ -1,0 +1,181 @@
+"""CPU tier: host-side logic of the product -- the C ABI surface, kernel selection, the query
+mask builder, the DP column functions (run on the host through tests/libhost_sim.so, same source
+as the CUDA kernels) and the multi-rank sharding (gloo, world_size 2)."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import refutil as R
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def _ensure_built():
+    lib = ROOT / "bgsa_b200" / "libbgsa_b200.so"
+    sim = ROOT / "tests" / "libhost_sim.so"
+    if not lib.exists() or not sim.exists():
+        subprocess.check_call(["make", "-s", "-j8", "-C", str(ROOT), "lib", "sim"])
+    return lib, sim
+
+
+@pytest.fixture(scope="module")
+def sim():
+    _, path = _ensure_built()
+    lib = C.CDLL(str(path))
+    lib.host_sim_align.restype = C.c_int
+    lib.host_sim_align.argtypes = [C.c_int] * 5 + [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p]
+    return lib
+
+
+def run_sim(sim, algo, scheme, K, L, q, s, sign=-1):
+    qc = np.ascontiguousarray(R.to_codes(q)); ss = np.ascontiguousarray(s)
+    out = np.zeros((q.shape[0], s.shape[0]), np.int16)
+    rc = sim.host_sim_align(algo, scheme, K, L, sign, qc.ctypes.data, q.shape[0], q.shape[1] - 1, ss.ctypes.data,
+                            s.shape[0], s.shape[1] - 1, out.ctypes.data)
+    return rc, out
+
+
+def _instances(macro):
+    text = (ROOT / "bgsa_b200" / "csrc" / "instances.h").read_text().replace("\\\n", " ")
+    body = re.search(r"#define %s\(X\)(.*)" % macro, text).group(1)
+    return [(int(a), int(b)) for a, b in re.findall(r"X\((\d+),\s*(\d+)\)", body)]
+
+
+def test_c_abi_exports_every_declared_symbol():
+    import bgsa_b200 as B
+    _ensure_built()
+    header = (ROOT / "include" / "bgsa_b200.h").read_text()
+    declared = set(re.findall(r"\b(bgsa_[a-z_0-9]+)\s*\(", header))
+    declared -= {"bgsa_status_t", "bgsa_algo_t", "bgsa_params_t", "bgsa_seq_t"}
+    assert declared == set(B.EXPORTED_SYMBOLS)
+    lib = B.load()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert b"sm_100a" in lib.bgsa_version()
+
+
+def test_no_cpu_fallback_and_error_codes():
+    import bgsa_b200 as B
+    import torch
+    p = B.Params.default(B.BITPAL_PACKED)
+    assert (p.match, p.mismatch, p.gap, p.threshold, p.myers_sign) == (2, -3, -5, 31, -1)
+    assert B.load().bgsa_result_size(B.BANDED_MYERS) == 1 and B.load().bgsa_result_size(B.MYERS_GLOBAL) == 2
+    # unsupported requests are rejected before any CUDA call
+    assert not B.supported(B.Params.default(B.BITPAL_PACKED, match=7, mismatch=-1, gap=-3), 100, 100)
+    assert not B.supported(B.Params.default(B.BANDED_MYERS, threshold=5), 100, 120)
+    assert not B.supported(B.Params.default(B.BANDED_MYERS, threshold=40), 100, 100)
+    assert not B.supported(B.Params.default(B.MYERS_GLOBAL), 40000, 100)
+    assert B.supported(B.Params.default(B.MYERS_GLOBAL), 32768, 100)
+    assert not B.supported(B.Params.default(B.MYERS_GLOBAL), 0, 100)
+    if not torch.cuda.is_available():
+        q = np.full((1, 11), 65, np.uint8); q[:, 10] = 10
+        with pytest.raises(B.BgsaError) as ei:
+            B.align_batch(p, q, np.repeat(q, 4, axis=0))
+        assert ei.value.code == 3          # BGSA_ERR_CUDA: the product never falls back to the CPU
+
+
+def test_kernel_selection_matches_baseline_configs():
+    import bgsa_b200 as B
+    assert B.kernel_name(B.Params.default(B.BITPAL_PACKED), 150, 150) == "align_kernel<BitpalPacked<2,-3,-5,K=5>,L=1>"
+    assert B.kernel_name(B.Params.default(B.BITPAL_PACKED), 5000, 5000) == "align_kernel<BitpalPacked<2,-3,-5,K=5>,L=32>"
+    assert B.kernel_name(B.Params.default(B.MYERS_SEMIGLOBAL), 1000, 1000) == "align_kernel<MyersAlgo<K=32,semiglobal>,L=1>"
+    assert B.kernel_name(B.Params.default(B.MYERS_GLOBAL), 500, 500) == "align_kernel<MyersAlgo<K=16,global>,L=1>"
+    assert B.kernel_name(B.Params.default(B.BANDED_MYERS, threshold=5), 100, 100) == "banded_kernel<u32>"
+    assert B.kernel_name(B.Params.default(B.BANDED_MYERS, threshold=31), 100, 100) == "banded_kernel<u64>"
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_myers_columns_on_host(sim, mode):
+    rng = np.random.default_rng(100 + mode)
+    for K, L in _instances("BGSA_MYERS_INSTANCES"):
+        cap = 32 * K * L
+        for ql in {cap, max(1, cap - 33)}:
+            if ql > 2600:
+                ql = int(rng.integers(cap // 2 + 1, min(cap, 2600) + 1)) if cap // 2 < 2600 else 0
+            if ql < 1:
+                continue
+            sl = int(rng.integers(max(1, ql // 3), ql + 40))
+            q = R.random_rows(rng, 1, ql, with_n=0.02)
+            s = R.random_rows(rng, 4, sl, with_n=0.02)
+            s[0, : min(ql, sl)] = q[0, : min(ql, sl)]
+            rc, got = run_sim(sim, mode, 0, K, L, q, s)
+            assert rc == 0
+            assert (got == R.oracle_batch(mode, q, s)).all(), (K, L, ql, sl)
+    # generator -m 1: +distance (Main.java:127-141)
+    q = R.random_rows(rng, 1, 90); s = R.random_rows(rng, 5, 80)
+    rc, got = run_sim(sim, mode, 0, 3, 1, q, s, sign=1)
+    assert rc == 0 and (got == -R.oracle_batch(mode, q, s)).all()
+
+
+@pytest.mark.parametrize("scheme,mig", [(0, (2, -3, -5)), (1, (1, -1, -1)), (2, (1, -3, -2))])
+@pytest.mark.parametrize("packed", [True, False])
+def test_bitpal_columns_on_host(sim, scheme, mig, packed):
+    rng = np.random.default_rng(200 + scheme)
+    M, I, G = mig
+    inst = _instances("BGSA_BITPAL_PACKED_INSTANCES" if packed else "BGSA_BITPAL_NONPACKED_INSTANCES")
+    for K, L in inst:
+        cap = min(32 * K * L, 1200 if packed else 700)
+        for ql in {cap, max(1, cap - 1)}:
+            sl = int(rng.integers(max(1, ql // 2), ql + 20))
+            q = R.random_rows(rng, 1, ql, with_n=0.02)
+            s = R.random_rows(rng, 3, sl, with_n=0.02)
+            s[0, : min(ql, sl)] = q[0, : min(ql, sl)]
+            rc, got = run_sim(sim, 3 if packed else 4, scheme, K, L, q, s)
+            assert rc == 0
+            assert (got == R.oracle_batch(R.ALGO_BITPAL_PACKED, q, s, M=M, I=I, G=G)).all(), (K, L, ql, sl)
+
+
+def test_shard_counts():
+    from bgsa_b200.sharding import shard_counts, shard_range
+    assert shard_counts(1_000_000, 8) == [124992] * 7 + [125056]
+    assert shard_counts(100, 8) == [0] * 7 + [100]
+    assert shard_counts(0, 2) == [0, 0]
+    for total in (1, 31, 32, 33, 1000, 12345):
+        for world in (1, 2, 3, 8):
+            counts = shard_counts(total, world)
+            assert sum(counts) == total and all(c % 32 == 0 for c in counts[:-1])
+            assert [shard_range(total, r, world)[1] for r in range(world)] == counts
+            assert shard_range(total, world - 1, world)[0] + counts[-1] == total
+
+
+_WORKER = r"""
+import os, sys
+sys.path.insert(0, {root!r}); sys.path.insert(0, {root!r} + "/tests"); sys.path.insert(0, {root!r} + "/tools")
+import numpy as np, torch, torch.distributed as dist
+import refutil as R, synth
+from bgsa_b200.sharding import shard_range
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=int(sys.argv[1]), world_size=2)
+rank, world = dist.get_rank(), dist.get_world_size()
+q, s = synth.make("C2", 1000)
+first, count = shard_range(s.shape[0], rank, world)
+# each rank scores its own contiguous range (here with the oracle standing in for the GPU) ...
+mine = R.oracle_batch(R.ALGO_BITPAL_PACKED, q, s[first:first + count])
+# ... and the scores are gathered to rank 0 in device-major order, no collective on the data path
+parts = [None] * world
+dist.gather_object((first, mine), parts if rank == 0 else None, dst=0)
+t = torch.tensor([float(count)]); dist.all_reduce(t)
+assert int(t.item()) == s.shape[0]
+if rank == 0:
+    full = np.concatenate([p[1] for p in sorted(parts, key=lambda p: p[0])], axis=1)
+    assert (full == R.oracle_batch(R.ALGO_BITPAL_PACKED, q, s)).all()
+    print("OK")
+dist.destroy_process_group()
+"""
+
+
+def test_two_rank_sharding_gloo(tmp_path):
+    import socket
+    sock = socket.socket(); sock.bind(("127.0.0.1", 0)); port = sock.getsockname()[1]; sock.close()
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER.format(root=str(ROOT), port=port))
+    procs = [subprocess.Popen([sys.executable, str(script), str(r)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+             for r in range(2)]
+    outs = [p.communicate(timeout=240)[0].decode() for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert "OK" in outs[0]
