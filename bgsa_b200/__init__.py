@@ -89,6 +89,7 @@ def load():
         "bgsa_launch_count": (i64, []),
         "bgsa_kernel_name": (i32, [PP, i32, i32, C.c_char_p, i32]),
         "bgsa_int_peak": (i32, [i32, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+        "bgsa_align_peq_chunk": (i32, [PP, vp, i32, vp, i32, i32, i32, i32, i32, i64, vp, i32]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)       # AttributeError here = the library does not export the ABI
@@ -101,7 +102,7 @@ EXPORTED_SYMBOLS = [
     "bgsa_version", "bgsa_last_error", "bgsa_device_count", "bgsa_params_default", "bgsa_result_size", "bgsa_supported",
     "bgsa_align_batch", "bgsa_align_batch_submit", "bgsa_align_batch_wait", "bgsa_malloc_host", "bgsa_free_host",
     "bgsa_packed_bytes", "bgsa_pack_subjects_device", "bgsa_align_device", "bgsa_launch_count", "bgsa_kernel_name",
-    "bgsa_int_peak",
+    "bgsa_int_peak", "bgsa_align_peq_chunk",
 ]
 
 

@@ -412,6 +412,49 @@ int bgsa_align_batch(const bgsa_params_t *p, const char *queries, int n_queries,
     return bgsa_align_batch_wait(device, 0);
 }
 
+// ---- per-chunk entry behind the reference's kernel symbols (include/align_core.h) -------------
+int bgsa_align_peq_chunk(const bgsa_params_t *p, const char *query, int query_len, const void *peq, int word_bytes,
+                         int v_num, int usable_bits, int word_num, int subject_len, int64_t n_subjects, void *results,
+                         int device) {
+    Plan plan;
+    int rc = make_plan(p, query_len, subject_len, &plan);
+    if (rc) return rc;
+    if (!query || !peq || !results || n_subjects < 0 || (word_bytes != 4 && word_bytes != 8) || v_num < 1 ||
+        usable_bits < 1 || usable_bits > 8 * word_bytes || word_num < 1 || n_subjects % v_num != 0)
+        return fail(BGSA_ERR_ARG, "bgsa_align_peq_chunk: bad argument");
+    DeviceCtx *ctx;
+    rc = get_ctx(device, &ctx);
+    if (rc) return rc;
+    if (n_subjects == 0) return BGSA_OK;
+    static std::mutex chunk_mu;                 // the reference calls its kernel from an OpenMP team
+    std::lock_guard<std::mutex> lk(chunk_mu);
+    Job &job = ctx->job[1];
+    Lane &l = job.lane[0];
+    const size_t peq_bytes = (size_t)word_bytes * 5 * word_num * (size_t)n_subjects;
+    const size_t esize = plan.result_size;
+    if ((rc = l.d_rows.ensure(peq_bytes))) return rc;
+    if ((rc = l.d_packed.ensure((size_t)packed_bytes(subject_len, n_subjects)))) return rc;
+    if ((rc = l.d_results.ensure(esize * (size_t)n_subjects))) return rc;
+    if ((rc = l.d_counters.ensure(sizeof(unsigned long long)))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(l.d_rows.p, peq, peq_bytes, cudaMemcpyHostToDevice, l.stream));
+    const int head = plan.algo == BGSA_BANDED_MYERS ? plan.e : 0;
+    cudaError_t e = launch_unpeq(plan.layout, word_bytes, l.d_rows.p, word_num, usable_bits, head, subject_len, n_subjects, v_num,
+                                 l.d_packed.p, ctx->sm_count, l.stream);
+    if (e != cudaSuccess) return fail(BGSA_ERR_CUDA, "unpeq kernel launch failed: %s", cudaGetErrorString(e));
+    g_launches.fetch_add(1);
+    std::vector<char> qrow(query, query + query_len);
+    qrow.push_back('\n');
+    const void *d_tab;
+    rc = stage_queries(job.qc, plan, qrow.data(), 1, query_len, subject_len, l.stream, &d_tab);
+    if (rc) return rc;
+    rc = run_align(plan, ctx->sm_count, d_tab, static_cast<unsigned long long *>(l.d_counters.p), 1, query_len, l.d_packed.p,
+                   subject_len, n_subjects, l.d_results.p, n_subjects, l.stream);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(results, l.d_results.p, esize * (size_t)n_subjects, cudaMemcpyDeviceToHost, l.stream));
+    CUDA_TRY(cudaStreamSynchronize(l.stream));
+    return BGSA_OK;
+}
+
 int bgsa_int_peak(int device, double *lane_ops_per_s, double *sm_clock_mhz) {
     if (!lane_ops_per_s) return fail(BGSA_ERR_ARG, "lane_ops_per_s is NULL");
     DeviceCtx *ctx;

@@ -79,8 +79,8 @@ cudaError_t launch_pack(int layout, const void *d_rows, int slen, long long coun
     return cudaGetLastError();
 }
 
-cudaError_t launch_unpeq(int wordbytes, const void *d_peq, int word_num, int usable, int slen, long long count,
-                         int vnum, void *d_packed, int sm_count, cudaStream_t stream) {
+cudaError_t launch_unpeq(int layout, int wordbytes, const void *d_peq, int word_num, int usable, int head, int slen,
+                         long long count, int vnum, void *d_packed, int sm_count, cudaStream_t stream) {
     PackedSubjects v = make_packed_view(d_packed, slen, count);
     if (v.ntiles == 0) return cudaSuccess;
     long long blocks = (v.ntiles + 3) / 4;
@@ -89,12 +89,11 @@ cudaError_t launch_unpeq(int wordbytes, const void *d_peq, int word_num, int usa
     auto codes = const_cast<uint4 *>(v.codes);
     auto nmask = const_cast<uint32_t *>(v.nmask);
     auto flags = const_cast<uint8_t *>(v.tile_has_n);
-    if (wordbytes == 8)
-        unpeq_kernel<uint64_t><<<(unsigned)blocks, 128, 0, stream>>>(static_cast<const uint64_t *>(d_peq), word_num, usable,
-                                                                     slen, count, codes, nmask, flags, v.ntiles, v.ku, v.kn, vnum);
-    else
-        unpeq_kernel<uint32_t><<<(unsigned)blocks, 128, 0, stream>>>(static_cast<const uint32_t *>(d_peq), word_num, usable,
-                                                                     slen, count, codes, nmask, flags, v.ntiles, v.ku, v.kn, vnum);
+#define UNPEQ(T, LAY) unpeq_kernel<T, LAY><<<(unsigned)blocks, 128, 0, stream>>>(static_cast<const T *>(d_peq), word_num, usable, \
+        head, slen, count, codes, nmask, flags, v.ntiles, v.ku, v.kn, vnum)
+    if (wordbytes == 8) { if (layout == LAYOUT_PLANES) UNPEQ(uint64_t, LAYOUT_PLANES); else UNPEQ(uint64_t, LAYOUT_CODES); }
+    else { if (layout == LAYOUT_PLANES) UNPEQ(uint32_t, LAYOUT_PLANES); else UNPEQ(uint32_t, LAYOUT_CODES); }
+#undef UNPEQ
     return cudaGetLastError();
 }
 

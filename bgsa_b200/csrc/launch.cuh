@@ -50,8 +50,8 @@ cudaError_t launch_bitpal_nonpacked(int scheme, int K, int L, const LaunchArgs &
 cudaError_t launch_banded(const LaunchArgs &a, const void *d_rows_table, int e);
 cudaError_t launch_pack(int layout, const void *d_rows, int slen, long long count, void *d_packed, int sm_count,
                         cudaStream_t stream);
-cudaError_t launch_unpeq(int wordbytes, const void *d_peq, int word_num, int usable, int slen, long long count,
-                         int vnum, void *d_packed, int sm_count, cudaStream_t stream);
+cudaError_t launch_unpeq(int layout, int wordbytes, const void *d_peq, int word_num, int usable, int head, int slen,
+                         long long count, int vnum, void *d_packed, int sm_count, cudaStream_t stream);
 cudaError_t launch_int_peak(int sm_count, int iters, unsigned int *d_sink, cudaStream_t stream);
 
 }  // namespace bgsa

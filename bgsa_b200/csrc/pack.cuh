@@ -101,11 +101,13 @@ pack_kernel(const uint8_t *__restrict__ rows, int slen, long long count, uint4 *
     }
 }
 
-// Peq -> tiles, for the per-chunk drop-in entry points (align_core.h): recovers the subject bases
-// from the reference's match masks.  peq layout: [subject][5][word_num] words of `wordbits` bits,
-// `usable` cells per word (63 or 64 for align_cpu, global.c:35-38).
-template <typename WordT>
-__global__ void unpeq_kernel(const WordT *__restrict__ peq, int word_num, int usable, int slen, long long count,
+// Peq -> tiles, for the per-chunk drop-in entry points (include/align_core.h): recovers the subject
+// bases from the reference's match masks.  Reference layout (global.c:25-70 and SIMD twins):
+// group g = subject / vnum, lane l = subject % vnum, word (c, j) at peq[((g*5 + c)*word_num + j)*vnum + l],
+// `usable` cells per word.  head > 0 selects the banded placement (banded/BGSA_CPU/global.c:45-82):
+// subject[0..head) at bits head+1.. of word 0, subject[head + i] at bit i%64 of word 1 + i/64.
+template <typename WordT, int LAYOUT>
+__global__ void unpeq_kernel(const WordT *__restrict__ peq, int word_num, int usable, int head, int slen, long long count,
                              uint4 *__restrict__ codes, uint32_t *__restrict__ nmask, uint8_t *__restrict__ tile_has_n,
                              long long ntiles, int ku, int kn, int vnum) {
     const int lane = threadIdx.x & 31;
@@ -114,30 +116,48 @@ __global__ void unpeq_kernel(const WordT *__restrict__ peq, int word_num, int us
     for (long long tile = warp_global; tile < ntiles; tile += nwarps) {
         const long long subject = tile * kTileSubjects + lane;
         const bool live = subject < count;
-        // reference SIMD layout: group g = subject / vnum, lane l = subject % vnum,
-        // word (c, j) of that subject at peq[((g*5 + c) * word_num + j) * vnum + l]
         const long long g = subject / vnum, l = subject % vnum;
         uint32_t any_n = 0u;
         for (int u = 0; u < ku; u++) {
-            uint32_t cw[4] = {0u, 0u, 0u, 0u};
-            uint32_t nb[2] = {0u, 0u};
+            uint32_t lo[2] = {0u, 0u}, hi[2] = {0u, 0u}, nb[2] = {0u, 0u};
             if (live) {
                 for (int i = 0; i < kBasesPerUnit; i++) {
                     const int pos = u * kBasesPerUnit + i;
                     if (pos >= slen) break;
-                    const int j = pos / usable, b = pos % usable;
+                    int j, bit;
+                    if (head > 0) {
+                        if (pos < head) { j = 0; bit = head + 1 + pos; }
+                        else { j = 1 + (pos - head) / usable; bit = (pos - head) % usable; }
+                    } else { j = pos / usable; bit = pos % usable; }
                     uint32_t code = 0u, isn = 0u;
 #pragma unroll
                     for (int c = 1; c < 5; c++) {
                         const WordT w = peq[((g * 5 + c) * word_num + j) * vnum + l];
-                        if ((w >> b) & 1) { if (c == 4) isn = 1u; else code = (uint32_t)c; }
+                        if ((w >> bit) & 1) { if (c == 4) isn = 1u; else code = (uint32_t)c; }
                     }
-                    cw[i >> 4] |= code << (2 * (i & 15));
+                    lo[i >> 5] |= (code & 1u) << (i & 31);
+                    hi[i >> 5] |= (code >> 1) << (i & 31);
                     nb[i >> 5] |= isn << (i & 31);
                 }
             }
             any_n |= nb[0] | nb[1];
-            codes[(tile * ku + u) * 32 + lane] = make_uint4(cw[0], cw[1], cw[2], cw[3]);
+            uint4 outv;
+            if (LAYOUT == LAYOUT_PLANES) {
+                outv = make_uint4(lo[0], hi[0], lo[1], hi[1]);
+            } else {
+                // interleave the planes back into 2-bit codes
+                auto spread = [](uint32_t x) {       // 16 low bits -> even bit positions
+                    x &= 0xffffu;
+                    x = (x | (x << 8)) & 0x00ff00ffu;
+                    x = (x | (x << 4)) & 0x0f0f0f0fu;
+                    x = (x | (x << 2)) & 0x33333333u;
+                    x = (x | (x << 1)) & 0x55555555u;
+                    return x;
+                };
+                outv = make_uint4(spread(lo[0]) | (spread(hi[0]) << 1), spread(lo[0] >> 16) | (spread(hi[0] >> 16) << 1),
+                                  spread(lo[1]) | (spread(hi[1]) << 1), spread(lo[1] >> 16) | (spread(hi[1] >> 16) << 1));
+            }
+            codes[(tile * ku + u) * 32 + lane] = outv;
             if (2 * u < kn) nmask[(tile * kn + 2 * u) * 32 + lane] = nb[0];
             if (2 * u + 1 < kn) nmask[(tile * kn + 2 * u + 1) * 32 + lane] = nb[1];
         }

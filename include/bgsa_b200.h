@@ -120,6 +120,17 @@ int64_t bgsa_launch_count(void);
 /* Name of the kernel instance bgsa_align_device would use, e.g. "bitpal_packed<2,-3,-5,K=5,L=1>". */
 int bgsa_kernel_name(const bgsa_params_t *p, int query_len, int subject_len, char *buf, int buflen);
 
+/* ---- per-chunk entry behind the reference's own kernel symbols ----------------------------- *
+ * What align_cpu / align_sse / align_avx / align_mic (original/BGSA_CPU/align_core.h:8 and twins)
+ * forward to, see include/align_core.h.  `peq` is the reference's match-mask block for
+ * n_subjects subjects: [group][5][word_num][v_num] words of word_bytes bytes with usable_bits
+ * cells per word (global.c:25-70); for BGSA_BANDED_MYERS the banded placement of
+ * banded/BGSA_CPU/global.c:45-82 is assumed.  `results` receives n_subjects scores in subject
+ * order.  Blocking, thread-safe (serialised). */
+int bgsa_align_peq_chunk(const bgsa_params_t *p, const char *query, int query_len, const void *peq, int word_bytes,
+                         int v_num, int usable_bits, int word_num, int subject_len, int64_t n_subjects, void *results,
+                         int device);
+
 /* ---- integer-pipe roofline probe ---------------------------------------------------------
  * Runs a LOP3/IADD3 throughput microbenchmark on `device` and reports lane-operations per
  * second on the INT32 ALU pipe (MEASURED_PEAKS.json has no integer figure). */
