@@ -3,11 +3,13 @@
 NVCC     ?= nvcc
 GCC      ?= gcc
 ARCH     := -gencode arch=compute_100a,code=sm_100a
-NVFLAGS  := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -Wall -Xcompiler -Wno-unused-function
+# EXTRA: additional nvcc flags for experiment builds, e.g. make lib BUILD=build/x LIB=bgsa_b200/libx.so EXTRA=-DBGSA_FMA_SHIFT=0
+EXTRA    ?=
+NVFLAGS  := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -Wall -Xcompiler -Wno-unused-function $(EXTRA)
 CSRC     := bgsa_b200/csrc
 HOST     := bgsa_b200/host
-BUILD    := build
-LIB      := bgsa_b200/libbgsa_b200.so
+BUILD    ?= build
+LIB      ?= bgsa_b200/libbgsa_b200.so
 
 HDRS := $(wildcard $(CSRC)/*.cuh $(CSRC)/*.h) include/bgsa_b200.h
 

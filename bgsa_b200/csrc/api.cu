@@ -221,9 +221,12 @@ int stage_queries(QueryCache &qc, const Plan &plan, const char *queries, int nq,
 }
 
 int run_align(const Plan &plan, int sm_count, const void *d_tab, unsigned long long *d_counters, int nq, int qlen,
-              const void *d_packed, int slen, int64_t count, void *d_results, int64_t result_stride, cudaStream_t stream) {
-    if (count == 0 || nq == 0) return BGSA_OK;
+              const void *d_packed, int slen, int64_t count, void *d_results, int64_t result_stride, cudaStream_t stream,
+              long long *resident_subjects = nullptr) {
+    if ((count == 0 || nq == 0) && !resident_subjects) return BGSA_OK;
     LaunchArgs a;
+    a.dry_run = resident_subjects != nullptr;
+    a.resident_subjects = resident_subjects;
     a.ps = make_packed_view(const_cast<void *>(d_packed), slen, count);
     a.d_peq = static_cast<const uint32_t *>(d_tab);
     a.n_queries = nq;
@@ -243,7 +246,7 @@ int run_align(const Plan &plan, int sm_count, const void *d_tab, unsigned long l
         default: return fail(BGSA_ERR_ARG, "unknown algorithm %d", plan.algo);
     }
     if (e != cudaSuccess) return fail(BGSA_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
-    g_launches.fetch_add(1);
+    if (!a.dry_run) g_launches.fetch_add(1);
     return BGSA_OK;
 }
 
@@ -367,8 +370,18 @@ int bgsa_align_batch_submit(const bgsa_params_t *p, const char *queries, int n_q
     if (rc) return rc;
     CUDA_TRY(cudaEventRecord(job.tab_ready, job.lane[0].stream));
     // chunking: tile-aligned, at most ~8 chunks, never below 32 Ki subjects (launch overheads)
-    int64_t chunk = (count + 7) / 8;
-    if (chunk < 32768) chunk = 32768;
+    // Chunking.  The persistent grid works on `quantum` subjects at once (resident warps x subjects per warp); a
+    // chunk that is a whole number of quanta keeps every warp busy for the same number of rounds, anything else
+    // leaves part of the GPU idle for a round.  Aim at ~6 chunks (enough to hide the H2D of all but the first).
+    long long quantum = 0;
+    rc = run_align(plan, ctx->sm_count, d_tab, nullptr, n_queries, query_len, nullptr, slen, 0, nullptr, 0, nullptr, &quantum);
+    if (rc) return rc;
+    if (quantum < kTileSubjects) quantum = kTileSubjects;
+    static const int kChunks = getenv("BGSA_CHUNKS") ? atoi(getenv("BGSA_CHUNKS")) : 6;   // tuning knob
+    int64_t rounds = (count / (kChunks > 0 ? kChunks : 1) + quantum / 2) / quantum;
+    if (rounds < 1) rounds = 1;
+    int64_t chunk = rounds * quantum;
+    if (chunk < 32768) chunk = (32768 + quantum - 1) / quantum * quantum;
     chunk = (chunk + kTileSubjects - 1) / kTileSubjects * kTileSubjects;
     int li = 0;
     for (int64_t off = 0; off < count; off += chunk, li = (li + 1) % kLanesPerJob) {

@@ -1,5 +1,7 @@
 // inst_misc.cu -- banded kernel instances, pack / unpeq kernels, algorithm dispatchers and the
 // INT32-pipe throughput probe.
+#include <cstdlib>
+
 #include "banded.cuh"
 #include "instances.h"
 #include "launch.cuh"
@@ -43,6 +45,10 @@ static cudaError_t launch_banded_t(const LaunchArgs &a, const void *d_rows_table
         if (err != cudaSuccess) return err;
         if (occ < 1) occ = 1;
     }
+    if (a.dry_run) {
+        if (a.resident_subjects) *a.resident_subjects = (long long)a.sm_count * occ * (THREADS / 32) * 32;
+        return cudaSuccess;
+    }
     cudaError_t err = cudaMemsetAsync(a.d_counters, 0, sizeof(unsigned long long) * a.n_queries, a.stream);
     if (err != cudaSuccess) return err;
     long long want = (a.ps.ntiles + 3) / 4;
@@ -60,23 +66,53 @@ cudaError_t launch_banded(const LaunchArgs &a, const void *d_rows_table, int e) 
 }
 
 // ---- pack ----------------------------------------------------------------------------------------
+// Streaming kernel (HBM rate) whenever a warp's strip fits shared memory; the simple lane-per-row
+// kernel otherwise (rows shorter than one 16-byte piece, or longer than ~17 kbp -- where packing is
+// < 0.1 % of the alignment time anyway).
+template <int LAYOUT>
+static cudaError_t launch_pack_t(const uint8_t *rows, int slen, long long count, const PackedSubjects &v, int sm_count,
+                                 cudaStream_t stream) {
+    auto codes = const_cast<uint4 *>(v.codes);
+    auto nmask = const_cast<uint32_t *>(v.nmask);
+    auto flags = const_cast<uint8_t *>(v.tile_has_n);
+    const int stride = slen + 1;
+    const size_t warp_bytes = sizeof(uint32_t) * (size_t)pack_warp_words(stride);
+    constexpr size_t kSmemMax = 200 * 1024;
+    static const bool simple_only = getenv("BGSA_PACK_SIMPLE") != nullptr;       // A/B knob
+    if (stride < 16 || warp_bytes > kSmemMax || simple_only) {
+        long long blocks = (v.ntiles + 3) / 4;
+        const long long cap = (long long)sm_count * 16;
+        if (blocks > cap) blocks = cap;
+        pack_kernel<LAYOUT><<<(unsigned)blocks, 128, 0, stream>>>(rows, slen, count, codes, nmask, flags, v.ntiles, v.ku, v.kn);
+        return cudaGetLastError();
+    }
+    auto kern = pack_stream_kernel<LAYOUT>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    const int warps = 4 * warp_bytes <= 96 * 1024 ? 4 : (2 * warp_bytes <= kSmemMax ? 2 : 1);
+    const size_t smem = warp_bytes * warps;
+    int occ = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, warps * 32, smem);
+    if (e != cudaSuccess) return e;
+    if (occ < 1) occ = 1;
+    long long blocks = (v.ntiles + warps - 1) / warps;
+    const long long cap = (long long)sm_count * occ;
+    if (blocks > cap) blocks = cap;
+    kern<<<(unsigned)blocks, warps * 32, smem, stream>>>(rows, slen, count, codes, nmask, flags, v.ntiles, v.ku, v.kn);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_pack(int layout, const void *d_rows, int slen, long long count, void *d_packed, int sm_count,
                         cudaStream_t stream) {
     PackedSubjects v = make_packed_view(d_packed, slen, count);
     if (v.ntiles == 0) return cudaSuccess;
-    long long blocks = (v.ntiles + 3) / 4;
-    const long long cap = (long long)sm_count * 16;
-    if (blocks > cap) blocks = cap;
-    auto codes = const_cast<uint4 *>(v.codes);
-    auto nmask = const_cast<uint32_t *>(v.nmask);
-    auto flags = const_cast<uint8_t *>(v.tile_has_n);
-    if (layout == LAYOUT_CODES)
-        pack_kernel<LAYOUT_CODES><<<(unsigned)blocks, 128, 0, stream>>>(static_cast<const uint8_t *>(d_rows), slen, count,
-                                                                        codes, nmask, flags, v.ntiles, v.ku, v.kn);
-    else
-        pack_kernel<LAYOUT_PLANES><<<(unsigned)blocks, 128, 0, stream>>>(static_cast<const uint8_t *>(d_rows), slen, count,
-                                                                         codes, nmask, flags, v.ntiles, v.ku, v.kn);
-    return cudaGetLastError();
+    const uint8_t *rows = static_cast<const uint8_t *>(d_rows);
+    return layout == LAYOUT_CODES ? launch_pack_t<LAYOUT_CODES>(rows, slen, count, v, sm_count, stream)
+                                  : launch_pack_t<LAYOUT_PLANES>(rows, slen, count, v, sm_count, stream);
 }
 
 cudaError_t launch_unpeq(int layout, int wordbytes, const void *d_peq, int word_num, int usable, int head, int slen,

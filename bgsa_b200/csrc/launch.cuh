@@ -15,6 +15,10 @@ struct LaunchArgs {
     unsigned long long *d_counters;  // [n_queries], zeroed by the launcher
     int sm_count;
     cudaStream_t stream;
+    // dry_run: do not launch, only report in *resident_subjects how many subjects the persistent
+    // grid works on at once (resident warps x subjects per warp) -- the host uses it to size chunks
+    bool dry_run = false;
+    long long *resident_subjects = nullptr;
 };
 
 constexpr int kAlignThreads = 128;
@@ -28,6 +32,10 @@ cudaError_t launch_align(const LaunchArgs &a, typename Algo::Params prm) {
         cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kAlignThreads, 0);
         if (e != cudaSuccess) return e;
         if (occ < 1) occ = 1;
+    }
+    if (a.dry_run) {
+        if (a.resident_subjects) *a.resident_subjects = (long long)a.sm_count * occ * (kAlignThreads / 32) * (32 / L);
+        return cudaSuccess;
     }
     cudaError_t e = cudaMemsetAsync(a.d_counters, 0, sizeof(unsigned long long) * a.n_queries, a.stream);
     if (e != cudaSuccess) return e;

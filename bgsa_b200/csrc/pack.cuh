@@ -101,6 +101,207 @@ pack_kernel(const uint8_t *__restrict__ rows, int slen, long long count, uint4 *
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// pack_stream_kernel -- the HBM-rate version of pack_kernel (same output, bit for bit).
+//
+// A tile (32 consecutive rows) is ONE contiguous run of 32*(slen+1) bytes.  One warp owns a tile:
+//   step 1 (stream order, coalesced): every lane loads 16-byte pieces of the run with LDG.128
+//          (4 in flight per lane), encodes 16 ASCII bytes -> one 32-bit word with SWAR logic (no
+//          per-byte work, see encode_piece) and stores it to the warp's shared-memory strip;
+//   step 2 (subject order): lane L cuts its own row out of the strip -- the row starts at an
+//          arbitrary bit offset, so every 128-bit unit is five LDS + four funnel shifts -- and
+//          stores it to the tile layout, 512 contiguous bytes per warp store.
+// No block-level synchronisation (__syncwarp only).  Traffic: slen+1 bytes in, ~slen/4 out per
+// subject; the N plane is written only for tiles that contain an 'N' (the alignment kernels never
+// read it otherwise, tile_has_n).
+//
+// SWAR encoding of one 32-bit word w = 4 ASCII bytes (exhaustively checked in
+// tests/test_host_logic.py::test_pack_swar_model):
+//   code  = (b1 ^ b2, b2 ^ b3) per byte b                A,C,G,T -> 0,1,2,3
+//   valid = byte in {A,C,G,T}  <=>  (b & 0xE8) == 0x40  and  b0 != b4  and  b4 ^ (~b2 | b1)
+//   the four 2-bit codes are gathered into one byte by an integer multiply (FMA pipe) whose
+//   partial products do not overlap, the bytes of four words are merged with PRMT.
+// A piece that holds anything else ('N', lower case, ...; the '\n' that ends a row is excused
+// by position) takes the exact per-byte path.  Alphabet: original/BGSA_CPU/global.c:9-15.
+// ---------------------------------------------------------------------------------------------
+constexpr int kPackUnroll = 4;
+
+__host__ __device__ constexpr int pack_phys(int idx) { return idx + (idx >> 5); }   // one pad word per 32: kills bank conflicts of power-of-two row pitches
+// shared-memory words one warp needs for rows of `stride` bytes
+__host__ __device__ inline int pack_strip_pieces(int stride) { return 2 * stride + 3; }          // ceil((15 + 32*stride)/16) + 1
+__host__ __device__ inline int pack_code_words(int stride) { return pack_phys(pack_strip_pieces(stride) + 8) + 1; }
+__host__ __device__ inline int pack_warp_words(int stride) { return pack_code_words(stride) + (pack_strip_pieces(stride) + 8 + 1) / 2 + 1; }
+
+__device__ __forceinline__ uint32_t shl_clamp(uint32_t v, uint32_t n) {    // PTX shl clamps n > 31 to "all bits out"
+    uint32_t d; asm("shl.b32 %0, %1, %2;" : "=r"(d) : "r"(v), "r"(n)); return d;
+}
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+    uint32_t d; asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel)); return d;
+}
+
+// The exact per-byte path (rare: only pieces that hold something besides A,C,G,T).  Kept out of the unrolled
+// streaming loop on purpose: a data-dependent branch inside that loop crashes ptxas 12.9 and bloats the hot path.
+template <int LAYOUT>
+__device__ __noinline__ uint2 encode_piece_exact(const uint4 v) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint32_t cw = 0u, nbits = 0u;
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        const uint32_t c = (w[i >> 2] >> (8 * (i & 3))) & 0xffu;
+        const uint32_t code = (c == 'C') ? 1u : (c == 'G') ? 2u : (c == 'T') ? 3u : 0u;
+        if (LAYOUT == LAYOUT_CODES) cw |= code << (2 * i);
+        else cw |= ((code & 1u) << i) | ((code >> 1) << (16 + i));
+        nbits |= (c == 'N' ? 1u : 0u) << i;
+    }
+    return make_uint2(cw, nbits);
+}
+
+// 16 ASCII bytes -> packed word; returns non-zero when the piece holds a byte outside {A,C,G,T} (then the word is
+// meaningless and encode_piece_exact must be used).  e = index of the row-end byte inside the piece (>= 16: none).
+// CODES : base i at bits 2i.   PLANES: low code bit of base i at bit i, high code bit at bit 16+i.
+template <int LAYOUT>
+__device__ __forceinline__ uint32_t encode_piece(const uint4 v, int e, uint32_t &cw) {
+    const uint32_t c06 = 0x06060606u, c40 = 0x40404040u, cE8 = 0xE8E8E8E8u, c10 = 0x10101010u;
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint32_t x[4], accbad = 0u;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        // Left shifts only where possible: they compile to IMAD.SHL (FMA pipe), the ALU pipe is this kernel's bound.
+        // code bits land at bits 1-2 of every byte, the two validity tests at bit 4.
+        const uint32_t s1 = w[j] >> 1, l2 = w[j] << 2, l3 = w[j] << 3, l4 = w[j] << 4;
+        x[j] = lop3<(LA ^ LB) & LC>(w[j], s1, c06);                          // (b1^b2, b2^b3) = code
+        const uint32_t v2 = lop3<LA ^ ((0xFF ^ LB) | LC)>(w[j], l2, l3);     // bit 4: b4 ^ (~b2 | b1)
+        const uint32_t g = lop3<(LA ^ LB) & LC>(w[j], l4, v2);               // bit 4: (b4 ^ b0) & v2
+        uint32_t bad = lop3<(LA ^ LB) & LC>(w[j], c40, cE8);                 // (b & 0xE8) != 0x40
+        bad = lop3<LA | ((0xFF ^ LB) & LC)>(bad, g, c10);
+        const uint32_t excuse = shl_clamp(0xffu, (uint32_t)(8 * e - 32 * j));     // the row-end byte may be anything
+        accbad = lop3<LA | (LB & (0xFF ^ LC))>(accbad, bad, excuse);
+    }
+    if (LAYOUT == LAYOUT_CODES) {
+        const uint32_t K = (1u << 23) | (1u << 17) | (1u << 11) | (1u << 5);
+        const uint32_t t01 = prmt(x[0] * K, x[1] * K, 0x0073u), t23 = prmt(x[2] * K, x[3] * K, 0x0073u);
+        cw = prmt(t01, t23, 0x5410u);
+    } else {
+        const uint32_t KL = (1u << 27) | (1u << 20) | (1u << 13) | (1u << 6);
+        uint32_t lo = 0u, hi = 0u;
+#pragma unroll
+        for (int j = 3; j >= 0; j--) {
+            lo = __funnelshift_l((x[j] & 0x02020202u) * KL, lo, 4);
+            hi = __funnelshift_l((x[j] & 0x04040404u) * (KL >> 1), hi, 4);
+        }
+        cw = lo | (hi << 16);
+    }
+    return accbad;
+}
+
+template <int LAYOUT>
+__global__ void __launch_bounds__(128)
+pack_stream_kernel(const uint8_t *__restrict__ rows, int slen, long long count, uint4 *__restrict__ codes,
+                   uint32_t *__restrict__ nmask, uint8_t *__restrict__ tile_has_n, long long ntiles, int ku, int kn) {
+    extern __shared__ __align__(16) uint32_t s_pack[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+    const int stride = slen + 1;
+    uint32_t *s_c = s_pack + warp * pack_warp_words(stride);
+    uint16_t *s_n = reinterpret_cast<uint16_t *>(s_c + pack_code_words(stride));
+    // tile starts are multiples of 32 bytes from `rows`: the misalignment of the run is the same for every tile
+    const int off = (int)(reinterpret_cast<uintptr_t>(rows) & 15);
+    const int inc = 512 % stride;                                   // advance of (position mod stride) per loop trip
+    int m0 = (16 * lane - off) % stride;                            // position of this lane's first piece inside its row
+    if (m0 < 0) m0 += stride;
+    const int base_pos = off + lane * stride;                       // strip position of this lane's own row
+    const int wi0 = base_pos >> 4, sub = base_pos & 15;
+
+    for (long long tile = (long long)blockIdx.x * warps + warp; tile < ntiles; tile += (long long)gridDim.x * warps) {
+        const long long first = tile * kTileSubjects;
+        const int live_rows = (int)min((long long)kTileSubjects, count - first);
+        const uint4 *src = reinterpret_cast<const uint4 *>(rows + first * stride - off);
+        const int npieces = (off + live_rows * stride + 15) >> 4;
+        // ---- step 1: stream order
+        uint32_t any_n = 0u;
+        int m = m0;
+        for (int p0 = lane; p0 < npieces; p0 += 32 * kPackUnroll) {
+            uint4 v[kPackUnroll];
+#pragma unroll
+            for (int k = 0; k < kPackUnroll; k++) {
+                const int p = p0 + 32 * k;
+                v[k] = p < npieces ? __ldg(src + p) : make_uint4(0x41414141u, 0x41414141u, 0x41414141u, 0x41414141u);
+            }
+            uint32_t redo = 0u;                                     // bit k: piece k needs the exact path
+#pragma unroll
+            for (int k = 0; k < kPackUnroll; k++) {
+                const int p = p0 + 32 * k;
+                uint32_t cw;
+                const uint32_t bad = encode_piece<LAYOUT>(v[k], slen - m, cw);
+                m += inc;
+                if (m >= stride) m -= stride;
+                if (p < npieces) {
+                    s_c[pack_phys(p)] = cw;
+                    s_n[p] = (uint16_t)0;
+                    redo |= (bad != 0u ? 1u : 0u) << k;
+                }
+            }
+            while (redo) {                                          // rare: 'N', lower case, ...
+                const int k = __ffs(redo) - 1;
+                redo &= redo - 1u;
+                const int p = p0 + 32 * k;
+                const uint2 r = encode_piece_exact<LAYOUT>(__ldg(src + p));
+                s_c[pack_phys(p)] = r.x;
+                s_n[p] = (uint16_t)r.y;
+                any_n |= r.y;
+            }
+        }
+        const bool tile_n = __ballot_sync(0xffffffffu, any_n != 0u) != 0u;
+        __syncwarp();
+        // ---- step 2: subject order
+        const bool live = lane < live_rows;
+        for (int u = 0; u < ku; u++) {
+            uint4 outv = make_uint4(0u, 0u, 0u, 0u);
+            if (live) {
+                uint32_t t[5];
+#pragma unroll
+                for (int i = 0; i < 5; i++) t[i] = s_c[pack_phys(wi0 + 4 * u + i)];
+                if (LAYOUT == LAYOUT_CODES) {
+                    const int sh = 2 * sub;
+                    outv.x = __funnelshift_r(t[0], t[1], sh); outv.y = __funnelshift_r(t[1], t[2], sh);
+                    outv.z = __funnelshift_r(t[2], t[3], sh); outv.w = __funnelshift_r(t[3], t[4], sh);
+                    const int nb = slen - u * kBasesPerUnit;          // bases of this unit that exist
+                    if (nb < kBasesPerUnit) {
+                        auto keep = [](int n) { return n >= 16 ? 0xffffffffu : (n <= 0 ? 0u : ((1u << (2 * n)) - 1u)); };
+                        outv.x &= keep(nb); outv.y &= keep(nb - 16); outv.z &= keep(nb - 32); outv.w &= keep(nb - 48);
+                    }
+                } else {
+                    // strip word = lo16 | hi16 << 16 per 16 bases
+                    const uint32_t lo01 = prmt(t[0], t[1], 0x5410u), lo23 = prmt(t[2], t[3], 0x5410u);
+                    const uint32_t hi01 = prmt(t[0], t[1], 0x7632u), hi23 = prmt(t[2], t[3], 0x7632u);
+                    outv.x = __funnelshift_r(lo01, lo23, sub); outv.y = __funnelshift_r(hi01, hi23, sub);
+                    outv.z = __funnelshift_r(lo23, t[4] & 0xffffu, sub); outv.w = __funnelshift_r(hi23, t[4] >> 16, sub);
+                    const int nb = slen - u * kBasesPerUnit;
+                    if (nb < kBasesPerUnit) {
+                        auto keep = [](int n) { return n >= 32 ? 0xffffffffu : (n <= 0 ? 0u : ((1u << n) - 1u)); };
+                        outv.x &= keep(nb); outv.y &= keep(nb); outv.z &= keep(nb - 32); outv.w &= keep(nb - 32);
+                    }
+                }
+            }
+            codes[(tile * ku + u) * 32 + lane] = outv;
+        }
+        if (tile_n) {
+            for (int k = 0; k < kn; k++) {
+                uint32_t nm = 0u;
+                if (live) {
+                    const int q = wi0 + 2 * k;
+                    const uint32_t a = (uint32_t)s_n[q] | ((uint32_t)s_n[q + 1] << 16), b = s_n[q + 2];
+                    nm = __funnelshift_r(a, b, sub);
+                    const int nb = slen - 32 * k;
+                    if (nb < 32) nm &= (1u << nb) - 1u;
+                }
+                nmask[(tile * kn + k) * 32 + lane] = nm;
+            }
+        }
+        if (lane == 0) tile_has_n[tile] = tile_n ? 1 : 0;
+        __syncwarp();      // the strip is rewritten by the next tile
+    }
+}
+
 // Peq -> tiles, for the per-chunk drop-in entry points (include/align_core.h): recovers the subject
 // bases from the reference's match masks.  Reference layout (global.c:25-70 and SIMD twins):
 // group g = subject / vnum, lane l = subject % vnum, word (c, j) at peq[((g*5 + c)*word_num + j)*vnum + l],

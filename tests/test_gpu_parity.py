@@ -250,3 +250,63 @@ def test_device_resident_api_matches_host_api(B):
     B.align_device(p, q, d_packed.data_ptr(), 150, s.shape[0], d_res.data_ptr(), s.shape[0], 0, st)
     torch.cuda.synchronize()
     assert (d_res.cpu().numpy()[None, :] == B.align_batch(p, q, s)).all()
+
+
+# ---- pack kernels: the packed tile layout itself (csrc/bgsa_common.cuh), against a numpy packer -----
+def _numpy_pack(rows, layout):
+    """rows [n, slen+1] ASCII -> (codes uint32 [ntiles, ku, 32, 4], nmask uint32 [ntiles, kn, 32], has_n [ntiles])."""
+    n, slen = rows.shape[0], rows.shape[1] - 1
+    ntiles, ku, kn = (n + 31) // 32, (slen + 63) // 64, (slen + 31) // 32
+    code = np.zeros(256, dtype=np.uint64)
+    code[ord("C")], code[ord("G")], code[ord("T")] = 1, 2, 3
+    c = np.zeros((ntiles * 32, ku * 64), dtype=np.uint64)
+    c[:n, :slen] = code[rows[:, :slen]]
+    isn = np.zeros((ntiles * 32, kn * 32), dtype=np.uint64)
+    isn[:n, :slen] = rows[:, :slen] == ord("N")
+    if layout == 0:      # base i of a unit at bits 2*(i%16) of word i/16
+        w = (c.reshape(ntiles, 32, ku, 4, 16) << (2 * np.arange(16, dtype=np.uint64))).sum(-1)
+    else:                # x,y = low/high planes of bases 0..31, z,w = of bases 32..63
+        b = c.reshape(ntiles, 32, ku, 2, 32)
+        lo = ((b & 1) << np.arange(32, dtype=np.uint64)).sum(-1)
+        hi = ((b >> 1) << np.arange(32, dtype=np.uint64)).sum(-1)
+        w = np.stack([lo[..., 0], hi[..., 0], lo[..., 1], hi[..., 1]], axis=-1)
+    codes = w.transpose(0, 2, 1, 3).astype(np.uint32)
+    nm = (isn.reshape(ntiles, 32, kn, 32) << np.arange(32, dtype=np.uint64)).sum(-1).transpose(0, 2, 1).astype(np.uint32)
+    return codes, nm, isn.reshape(ntiles, -1).any(axis=1)
+
+
+@pytest.mark.parametrize("slen,n", [(150, 1000), (100, 4099), (1000, 130), (15, 77), (16, 64), (31, 33), (127, 97), (511, 65),
+                                    (63, 32), (64, 31), (65, 1), (5000, 40), (3, 50), (255, 200), (4095, 37)])
+@pytest.mark.parametrize("layout_algo", [0, 2])
+def test_pack_kernels_bit_exact(B, slen, n, layout_algo):
+    """Both pack kernels (streaming, and the simple one used for tiny / huge rows) against numpy: clean
+    rows, rows with N / lower case / arbitrary bytes, and a row buffer that is not 16-byte aligned."""
+    import torch
+    rng = np.random.default_rng(slen * 7 + n)
+    p = B.Params.default(layout_algo, threshold=5)
+    layout = 1 if layout_algo == 2 else 0
+    for variant in ("clean", "dirty"):
+        rows = R.random_rows(rng, n, slen, with_n=0.0 if variant == "clean" else 0.02)
+        if variant == "dirty":
+            junk = rng.random(rows[:, :slen].shape) < 0.01
+            rows[:, :slen][junk] = rng.integers(0, 256, size=int(junk.sum()), dtype=np.uint8)
+            rows[::7, slen] = 13          # a row end that is not a newline
+            rows[n // 2, :slen] = ord("A")
+        for shift in (0, 5):
+            buf = torch.zeros(rows.size + 64, dtype=torch.uint8, device="cuda")
+            buf[shift:shift + rows.size] = torch.from_numpy(rows.reshape(-1)).cuda()
+            nbytes = B.packed_bytes(slen, n)
+            d_packed = torch.full((nbytes,), 0xA5, dtype=torch.uint8, device="cuda")
+            B.pack_subjects_device(p, buf.data_ptr() + shift, slen, n, d_packed.data_ptr())
+            torch.cuda.synchronize()
+            raw = d_packed.cpu().numpy()
+            ntiles, ku, kn = (n + 31) // 32, (slen + 63) // 64, (slen + 31) // 32
+            up = lambda x: (x + 255) // 256 * 256
+            codes = raw[: ntiles * ku * 512].view(np.uint32).reshape(ntiles, ku, 32, 4)
+            o1 = up(ntiles * ku * 512)
+            nm = raw[o1: o1 + ntiles * kn * 128].view(np.uint32).reshape(ntiles, kn, 32)
+            flags = raw[o1 + up(ntiles * kn * 128): o1 + up(ntiles * kn * 128) + ntiles]
+            ec, en, ef = _numpy_pack(rows, layout)
+            assert (codes == ec).all(), (variant, shift)
+            assert ((flags != 0) == ef).all(), (variant, shift)
+            assert (nm[ef] == en[ef]).all(), (variant, shift)      # the N plane is only defined for flagged tiles

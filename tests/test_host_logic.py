@@ -179,3 +179,34 @@ def test_two_rank_sharding_gloo(tmp_path):
     outs = [p.communicate(timeout=240)[0].decode() for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
     assert "OK" in outs[0]
+
+
+# ---- pack: SWAR encoder of csrc/pack.cuh::encode_piece, modelled in Python, exhaustive per byte ------
+def _swar_word(w):
+    M = 0xFFFFFFFF
+    s1, l2, l3, l4 = w >> 1, (w << 2) & M, (w << 3) & M, (w << 4) & M
+    x = (w ^ s1) & 0x06060606
+    v2 = (w ^ ((~l2 & M) | l3)) & M
+    g = (w ^ l4) & v2
+    bad = ((w ^ 0x40404040) & 0xE8E8E8E8) | (~g & 0x10101010)
+    K = (1 << 23) | (1 << 17) | (1 << 11) | (1 << 5)
+    KL = (1 << 27) | (1 << 20) | (1 << 13) | (1 << 6)
+    return bad, ((x * K) & M) >> 24, (((x & 0x02020202) * KL) & M) >> 28, (((x & 0x04040404) * (KL >> 1)) & M) >> 28
+
+
+def test_pack_swar_model():
+    code = {0x41: 0, 0x43: 1, 0x47: 2, 0x54: 3}
+    rng = np.random.default_rng(3)
+    for pos in range(4):
+        for c in range(256):
+            for trial in range(12):
+                bs = [int(b) for b in (rng.choice([0x41, 0x43, 0x47, 0x54], 4) if trial % 3 else rng.integers(0, 256, 4))]
+                bs[pos] = c
+                w = sum(b << (8 * i) for i, b in enumerate(bs))
+                bad, c8, lo4, hi4 = _swar_word(w)
+                for i, b in enumerate(bs):      # the validity test is exact per byte
+                    assert (((bad >> (8 * i)) & 0xFF) == 0) == (b in code)
+                if all(b in code for b in bs):  # and the gathered codes / planes are right when it passes
+                    assert c8 == sum(code[b] << (2 * i) for i, b in enumerate(bs))
+                    assert lo4 == sum((code[b] & 1) << i for i, b in enumerate(bs))
+                    assert hi4 == sum((code[b] >> 1) << i for i, b in enumerate(bs))
