@@ -7,7 +7,8 @@
 //     static void init(State&);
 //     template <bool CARRY> static uint32_t column(State&, const uint32_t* peq_row, uint32_t cin);
 //         one DP column = one subject base.  With CARRY the low word's carry-ins come from `cin`
-//         (bits 3.. , layout private to the algorithm) and the carry-outs are returned.
+//         (a CarryIn stream, top-aligned, bits 0..2 ignored) and the carry-outs are returned as
+//         a CarryOut stream with bits 0..2 clear.
 //     static constexpr uint32_t kBoundary;            // carry-in bits at the top row (lane 0)
 //     static Partial partial(const State&, int first_bit, int qlen);   // per-lane score pieces
 //     static int final_score(sum, min_prefix, qlen, slen, Params);     // 32-bit score
@@ -28,6 +29,8 @@
 // subjects from a global counter (no tail imbalance, no block-level barrier after start-up).
 // HBM traffic per subject: slen/4 bytes in, 2 bytes out.
 #pragma once
+
+#include <type_traits>
 
 #include "bgsa_common.cuh"
 
@@ -84,20 +87,24 @@ align_kernel(PackedSubjects ps, const uint32_t *__restrict__ g_peq, int qlen, in
             typename Algo::State state;
             Algo::init(state);
             uint32_t packet = 0u;                            // what this lane hands to lane rank+1
-            int tcol = -rank;                                // column this lane works on at the next step
+            int t = 0;                                       // wavefront step = column of lane 0 (checked steps only)
 
-            // one wavefront step: receive (base, carries) from the lane above, do one column
-            auto step = [&](uint32_t head_base) {
+            // One wavefront step: receive (base, carries) from the lane above, do one column.  Lane r works
+            // on column t - r, which exists for every lane once t >= L-1 and while t < slen: only the L-1
+            // steps at either end of a subject need the range check.
+            auto step = [&](uint32_t head_base, auto checked) {
                 if (L == 1) {
                     (void)Algo::template column<false>(state, my_peq + head_base * STRIDE, 0u);
                 } else {
                     uint32_t recv = __shfl_up_sync(0xffffffffu, packet, 1, L);
                     if (rank == 0) recv = Algo::kBoundary | head_base;
-                    if ((unsigned)tcol < (unsigned)slen)
+                    if (!decltype(checked)::value || (unsigned)(t - rank) < (unsigned)slen)
                         packet = Algo::template column<true>(state, my_peq + (recv & 7u) * STRIDE, recv) | (recv & 7u);
-                    tcol++;
+                    if (decltype(checked)::value) t++;
                 }
             };
+            constexpr std::true_type kChecked{};
+            constexpr std::false_type kFree{};
 
             for (int sg = 0; sg < nstages; sg++) {
                 // prefetch the following stage (same unit, or the first stage of the next unit)
@@ -120,12 +127,20 @@ align_kernel(PackedSubjects ps, const uint32_t *__restrict__ g_peq, int qlen, in
                     for (int w = 0; w < 4; w++) {
                         const int nb = min(16, slen - base0 - 16 * w);
                         uint32_t word = (w == 0) ? v.x : (w == 1) ? v.y : (w == 2) ? v.z : v.w;
-                        if (!with_n) {
+                        if (!with_n && (L == 1 || base0 + 16 * w >= L - 1)) {
 #pragma unroll (UNROLL)
                             for (int i = 0; i < nb; i++) {
                                 const uint32_t c = word & 3u;
                                 word >>= 2;
-                                step(c);
+                                step(c, kFree);
+                            }
+                            t += nb > 0 ? nb : 0;
+                        } else if (!with_n) {   // first L-1 columns of a subject: the wavefront is filling
+#pragma unroll 1
+                            for (int i = 0; i < nb; i++) {
+                                const uint32_t c = word & 3u;
+                                word >>= 2;
+                                step(c, kChecked);
                             }
                         } else {   // rare path: the tile contains at least one 'N'
                             uint32_t nbits = ((w < 2) ? n0 : n1) >> (16 * (w & 1));
@@ -134,7 +149,7 @@ align_kernel(PackedSubjects ps, const uint32_t *__restrict__ g_peq, int qlen, in
                                 const uint32_t c = (word & 3u) | ((nbits & 1u) << 2);
                                 word >>= 2;
                                 nbits >>= 1;
-                                step(c);
+                                step(c, kChecked);
                             }
                         }
                     }
@@ -144,7 +159,7 @@ align_kernel(PackedSubjects ps, const uint32_t *__restrict__ g_peq, int qlen, in
             }
             if (L > 1) {
 #pragma unroll 1
-                for (int i = 0; i < L - 1; i++) step(0u);    // drain the wavefront
+                for (int i = 0; i < L - 1; i++) step(0u, kChecked);    // drain the wavefront
             }
             // ---- score: combine the per-lane pieces of the final delta vector
             Partial p = Algo::partial(state, rank * K * 32, qlen);

@@ -53,11 +53,23 @@ struct SchemeRow { int id, M, I, G; };
 const SchemeRow kSchemes[] = {BGSA_SCHEMES(X)};
 #undef X
 
+// Cheapest instance that fits the query: cost of one DP column of one subject in ALU instructions
+// = L lanes x (K words x ops per word + wavefront hand-over).  Ties go to fewer lanes.
+// BGSA_FORCE_KL="K,L" pins an instance (A/B measurements; must fit the query).
 template <size_t N>
-bool pick(const KL (&table)[N], int qlen, KL *out) {
-    for (size_t i = 0; i < N; i++)
-        if (32 * table[i].K * table[i].L >= qlen) { *out = table[i]; return true; }
-    return false;
+bool pick(const KL (&table)[N], int qlen, int ops_per_word, int handover, KL *out) {
+    static const char *force = getenv("BGSA_FORCE_KL");
+    int fk = 0, fl = 0;
+    if (force && sscanf(force, "%d,%d", &fk, &fl) != 2) fk = fl = 0;
+    long best = -1;
+    for (size_t i = 0; i < N; i++) {
+        const KL c = table[i];
+        if (32 * c.K * c.L < qlen) continue;
+        if (fk && c.K == fk && c.L == fl) { *out = c; return true; }
+        const long cost = (long)c.L * (c.K * ops_per_word + (c.L > 1 ? handover : 0));
+        if (best < 0 || cost < best) { best = cost; *out = c; }
+    }
+    return best >= 0;
 }
 int find_scheme(int M, int I, int G) {
     for (const SchemeRow &s : kSchemes) if (s.M == M && s.I == I && s.G == G) return s.id;
@@ -88,7 +100,7 @@ int make_plan(const bgsa_params_t *p, int qlen, int slen, Plan *plan) {
         case BGSA_MYERS_GLOBAL:
         case BGSA_MYERS_SEMIGLOBAL:
             if (plan->sign != -1 && plan->sign != 1) return fail(BGSA_ERR_ARG, "myers_sign must be -1, 0 or +1");
-            if (!pick(kMyersTable, qlen, &plan->kl))
+            if (!pick(kMyersTable, qlen, 10, 20, &plan->kl))
                 return fail(BGSA_ERR_UNSUPPORTED, "Myers: query length %d exceeds the largest kernel instance (32768)", qlen);
             return BGSA_OK;
         case BGSA_BITPAL_PACKED:
@@ -97,7 +109,8 @@ int make_plan(const bgsa_params_t *p, int qlen, int slen, Plan *plan) {
             if (plan->scheme < 0)
                 return fail(BGSA_ERR_UNSUPPORTED, "BitPAl: scoring scheme (%d,%d,%d) has no kernel instance (see csrc/instances.h)",
                             p->match, p->mismatch, p->gap);
-            const bool ok = p->algo == BGSA_BITPAL_PACKED ? pick(kPackedTable, qlen, &plan->kl) : pick(kNonPackedTable, qlen, &plan->kl);
+            const bool ok = p->algo == BGSA_BITPAL_PACKED ? pick(kPackedTable, qlen, 77, 34, &plan->kl)
+                                                          : pick(kNonPackedTable, qlen, 185, 45, &plan->kl);
             if (!ok) return fail(BGSA_ERR_UNSUPPORTED, "BitPAl: query length %d exceeds the largest kernel instance", qlen);
             return BGSA_OK;
         }

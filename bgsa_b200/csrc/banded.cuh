@@ -53,7 +53,7 @@ banded_kernel(PackedSubjects ps, const BandedRow *__restrict__ g_rows, int qlen,
     const BandedRow *rows = g_rows + (size_t)q * qlen;
     unsigned long long *counter = counters + q;
     int8_t *out = results + (long long)q * result_stride;
-    const int slen = ps.slen, ku = ps.ku;
+    const int ku = ps.ku;
     const int sh = e + 1;                                     // plane index u = i + e + 1
     const int C = qlen <= 64 ? qlen : max(64, qlen - e);      // rows done at the last checkpoint
     const int max_err = 2 * e + 1;                            // threshold + h_threshold + 1 (:114)

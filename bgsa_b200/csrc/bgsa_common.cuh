@@ -129,23 +129,34 @@ BGSA_HD uint32_t addc(uint32_t a, uint32_t b) {
 #endif
 }
 
-// out = a + b + cin over K words; returns carry out (0/1).  HAS_CIN / WANT_COUT are compile time
-// so the thread-per-subject kernels (no neighbours) pay exactly K instructions.
-template <int K, bool HAS_CIN, bool WANT_COUT>
-BGSA_HD uint32_t add_chain(uint32_t (&out)[K], const uint32_t (&a)[K], const uint32_t (&b)[K],
-                                              uint32_t cin) {
-    if (HAS_CIN) {
-        (void)add_cc(cin, 0xffffffffu);          // CF := (cin != 0)
-        out[0] = addc_cc(a[0], b[0]);
-    } else {
-        out[0] = add_cc(a[0], b[0]);
-    }
+// out = a + b (+ CF) over K words; the carry out stays in the hardware flag.  CF_IN: the caller has
+// just loaded the flag (CarryIn::to_cf); otherwise the chain starts with a plain add.  The
+// thread-per-subject kernels (no neighbours) pay exactly K instructions.
+template <int K, bool CF_IN>
+BGSA_HD void add_chain(uint32_t (&out)[K], const uint32_t (&a)[K], const uint32_t (&b)[K]) {
+    out[0] = CF_IN ? addc_cc(a[0], b[0]) : add_cc(a[0], b[0]);
 #pragma unroll
     for (int j = 1; j < K; j++) out[j] = addc_cc(a[j], b[j]);
-    uint32_t cout = 0;
-    if (WANT_COUT) cout = addc(0u, 0u);
-    return cout;
 }
+
+// Carry stream between neighbouring lanes of a wavefront group (align_kernel.cuh): the bits a lane
+// hands down (add carries, shift-in bits) travel in ONE 32-bit word, top-aligned, in the order the
+// receiver consumes them, the subject base in bits 0..2.  One instruction per bit on either side:
+//   receiver: add.cc w,w   moves the next bit into the hardware carry flag AND advances the word;
+//             a shift-in bit is used in place (funnel shifts only look at bit 31), then w += w.
+//   sender  : addc w,w     appends the carry flag;  funnel-shift appends the top bit of a vector.
+struct CarryIn {
+    uint32_t w;
+    BGSA_HD explicit CarryIn(uint32_t recv) : w(recv) {}
+    BGSA_HD void to_cf() { w = add_cc(w, w); }                      // CF := next bit
+    BGSA_HD uint32_t top() { const uint32_t t = w; w += w; return t; }  // next bit at bit 31 of the result
+};
+struct CarryOut {
+    uint32_t w = 0u;
+    BGSA_HD void push_cf() { w = addc(w, w); }                      // append CF
+    BGSA_HD void push_top(uint32_t v) { w = shl1_carry(v, w); }     // append bit 31 of v
+    template <int NBITS> BGSA_HD uint32_t finish() const { static_assert(NBITS <= 29, "carry word overflow"); return w << (32 - NBITS); }
+};
 
 // ---------------------------------------------------------------------------------------------
 // mbarrier + 1-D bulk async copy (TMA engine, SASS UBLKCP) for staging subject tiles

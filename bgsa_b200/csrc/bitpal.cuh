@@ -75,15 +75,16 @@ struct BitpalPacked {
             for (int j = 0; j < K; j++) s.d[b][j] = 0u;      // global start: every delta = G
     }
 
-    // carry word layout (bits above the 3-bit base): NH add carries (chain c at bit 3+c), NH-1
-    // shift-in bits of the init vectors (class c at bit 3+NH+c), NB shift-in bits of the e planes.
-    static constexpr int kAddBit = 3, kInitBit = 3 + NH, kEBit = 3 + NH + (NH > 0 ? NH - 1 : 0);
-    static_assert(kEBit + NB <= 32, "carry word overflow");
+    // carry stream (CarryIn/CarryOut, consumption order): add carry of class A; then for every lower
+    // high class, top down: shift-in bit of its init vector, its add carry; then the NB shift-in
+    // bits of the e planes.
+    static constexpr int kCarryBits = NH + (NH > 0 ? NH - 1 : 0) + NB;
     static constexpr uint32_t kBoundary = 0u;            // global top row: e_0 = 0, nothing propagates in
 
     template <bool CARRY>
     static BGSA_HD uint32_t column(State &s, const uint32_t *row, uint32_t cin) {
-        uint32_t cout = 0u;
+        CarryIn in(cin);
+        CarryOut out;
         uint32_t eq[(K + 3) / 4 * 4];
 #pragma unroll
         for (int j = 0; j < (K + 3) / 4; j++) {
@@ -114,8 +115,9 @@ struct BitpalPacked {
             uint32_t a0[K], sum[K];
 #pragma unroll
             for (int j = 0; j < K; j++) a0[j] = Z[j] & eq[j];
-            const uint32_t co = add_chain<K, CARRY, CARRY>(sum, a0, Z, cin & (1u << (kAddBit + NH - 1)));
-            if (CARRY) cout |= co << (kAddBit + NH - 1);
+            if (CARRY) in.to_cf();
+            add_chain<K, CARRY>(sum, a0, Z);
+            if (CARRY) out.push_cf();
 #pragma unroll
             for (int j = 0; j < K; j++) Y[NH - 1][j] = (sum[j] ^ remain[j]) | eq[j];   // e_{p-1} == A, or match
 #pragma unroll
@@ -128,11 +130,12 @@ struct BitpalPacked {
                     for (int dl = 1; c + dl <= NH - 1; dl++) v |= D[dl][j] & Y[c + dl][j];
                     init[j] = v;                              // e_p == k at a position with d != 0
                 }
+                const uint32_t sin = CARRY ? in.top() : 0u;
 #pragma unroll
-                for (int j = 0; j < K; j++)
-                    sh[j] = shl1_carry(j ? init[j - 1] : (CARRY ? cin << (31 - (kInitBit + c)) : 0u), init[j]);
-                const uint32_t co2 = add_chain<K, CARRY, CARRY>(sum, sh, remain, cin & (1u << (kAddBit + c)));
-                if (CARRY) cout |= (co2 << (kAddBit + c)) | ((init[K - 1] >> 31) << (kInitBit + c));
+                for (int j = 0; j < K; j++) sh[j] = shl1_carry(j ? init[j - 1] : sin, init[j]);
+                if (CARRY) { out.push_top(init[K - 1]); in.to_cf(); }
+                add_chain<K, CARRY>(sum, sh, remain);
+                if (CARRY) out.push_cf();
 #pragma unroll
                 for (int j = 0; j < K; j++) Y[c][j] = (sum[j] ^ remain[j]) & ~eq[j];
             }
@@ -140,7 +143,7 @@ struct BitpalPacked {
         // ---- binary planes of y, then e = max(0, y - d), T = max(y, d), d' = T - (e << 1)
         uint32_t e_prev[NB];
 #pragma unroll
-        for (int b = 0; b < NB; b++) e_prev[b] = CARRY ? cin << (31 - (kEBit + b)) : 0u;   // e_0 = 0: global top row
+        for (int b = 0; b < NB; b++) e_prev[b] = CARRY ? in.top() : 0u;   // e_0 = 0: global top row
 #pragma unroll
         for (int j = 0; j < K; j++) {
             uint32_t hi = 0u;
@@ -182,9 +185,9 @@ struct BitpalPacked {
         }
         if (CARRY) {
 #pragma unroll
-            for (int b = 0; b < NB; b++) cout |= (e_prev[b] >> 31) << (kEBit + b);
+            for (int b = 0; b < NB; b++) out.push_top(e_prev[b]);
         }
-        return cout;
+        return CARRY ? out.template finish<kCarryBits>() : 0u;
     }
 
     static BGSA_HD Partial partial(const State &s, int first_bit, int qlen) {
@@ -221,15 +224,15 @@ struct BitpalNonPacked {
             for (int j = 0; j < K; j++) s.d[v][j] = 0u;
     }
 
-    // carry word layout: add carry of class k (B < k <= A) at bit 3 + (k-B-1); shift-in bit of
-    // the init vector of class k (1 <= k < A) at bit 3 + NH + (k-1).
-    static constexpr int kAddBit = 3, kInitBit = 3 + NH;
-    static_assert(kInitBit + A - 1 <= 32, "carry word overflow");
+    // carry stream (consumption order): add carry of class A; for k = A-1 .. B+1: shift-in bit of
+    // init_k, add carry of class k; for k = B .. 1: shift-in bit of init_k.
+    static constexpr int kCarryBits = NH + (A - 1);
     static constexpr uint32_t kBoundary = 0u;
 
     template <bool CARRY>
     static BGSA_HD uint32_t column(State &s, const uint32_t *row, uint32_t cin) {
-        uint32_t cout = 0u;
+        CarryIn in(cin);
+        CarryOut out;
         uint32_t eq[(K + 3) / 4 * 4];
 #pragma unroll
         for (int j = 0; j < (K + 3) / 4; j++) {
@@ -247,7 +250,6 @@ struct BitpalNonPacked {
         }
         // DV(v, j) = [d_p == v]
 #define DV(v, j) (((v) == 0) ? Z[j] : s.d[((v) > 0 ? (v) : 1) - 1][j])
-#define SHIFT_IN(k) (CARRY ? cin << (31 - (kInitBit + (k) - 1)) : 0u)
         // X[v][j] = [e_{p-1} == v] for v = 1..A (shifted form), built class by class.
         // [y_p == v]: v == A -> X[A] | match ; B < v < A -> X[v] & ~match ; v == B -> rest.
         uint32_t X[A + 1][K];
@@ -255,8 +257,9 @@ struct BitpalNonPacked {
             uint32_t a0[K], sum[K];
 #pragma unroll
             for (int j = 0; j < K; j++) a0[j] = Z[j] & eq[j];
-            const uint32_t co = add_chain<K, CARRY, CARRY>(sum, a0, Z, cin & (1u << (kAddBit + NH - 1)));
-            if (CARRY) cout |= co << (kAddBit + NH - 1);
+            if (CARRY) in.to_cf();
+            add_chain<K, CARRY>(sum, a0, Z);
+            if (CARRY) out.push_cf();
 #pragma unroll
             for (int j = 0; j < K; j++) X[A][j] = sum[j] ^ remain[j];
 #pragma unroll
@@ -269,10 +272,12 @@ struct BitpalNonPacked {
                     for (int h = A - 1; h > k; h--) v |= DV(h - k, j) & (X[h][j] & ~eq[j]);
                     init[j] = v;
                 }
+                const uint32_t sin = CARRY ? in.top() : 0u;
 #pragma unroll
-                for (int j = 0; j < K; j++) sh[j] = shl1_carry(j ? init[j - 1] : SHIFT_IN(k), init[j]);
-                const uint32_t co2 = add_chain<K, CARRY, CARRY>(sum, sh, remain, cin & (1u << (kAddBit + k - B - 1)));
-                if (CARRY) cout |= (co2 << (kAddBit + k - B - 1)) | ((init[K - 1] >> 31) << (kInitBit + k - 1));
+                for (int j = 0; j < K; j++) sh[j] = shl1_carry(j ? init[j - 1] : sin, init[j]);
+                if (CARRY) { out.push_top(init[K - 1]); in.to_cf(); }
+                add_chain<K, CARRY>(sum, sh, remain);
+                if (CARRY) out.push_cf();
 #pragma unroll
                 for (int j = 0; j < K; j++) X[k][j] = sum[j] ^ remain[j];
             }
@@ -297,12 +302,12 @@ struct BitpalNonPacked {
                 v |= DV(B - k, j) & rest[j];
                 init[j] = v;
             }
-            if (CARRY) cout |= (init[K - 1] >> 31) << (kInitBit + k - 1);
+            const uint32_t sin = CARRY ? in.top() : 0u;
+            if (CARRY) out.push_top(init[K - 1]);
 #pragma unroll
-            for (int j = 0; j < K; j++) X[k][j] = shl1_carry(j ? init[j - 1] : SHIFT_IN(k), init[j]);
+            for (int j = 0; j < K; j++) X[k][j] = shl1_carry(j ? init[j - 1] : sin, init[j]);
         }
 #undef DV
-#undef SHIFT_IN
         // X0 = [e_{p-1} == 0]
         uint32_t X0[K];
 #pragma unroll
@@ -334,7 +339,7 @@ struct BitpalNonPacked {
 #pragma unroll
             for (int k = 0; k < A; k++) s.d[k][j] = nd[k];
         }
-        return cout;
+        return CARRY ? out.template finish<kCarryBits>() : 0u;
     }
 
     static BGSA_HD Partial partial(const State &s, int first_bit, int qlen) {

@@ -4,18 +4,22 @@
 // (generator/.../Main.java:240-315).  Here every combination is a C++ template instance selected
 // at run time; adding a scoring scheme or a geometry is one line in the tables below.
 // X(K, L): K 32-bit words per lane, L lanes per subject; serves queries up to 32*K*L bases.
-// Tables are ordered by preference: the first entry with 32*K*L >= query_len is used.
+// Among the instances that fit a query the cheapest is used (api.cu pick(): L * (K * ops per word
+// + per-step wavefront overhead)): wide lanes amortise the carry hand-over, few lanes waste less
+// of the last word.
 #pragma once
 
 // Myers global / semi-global
 #define BGSA_MYERS_INSTANCES(X)                                                              \
     X(1, 1) X(2, 1) X(3, 1) X(4, 1) X(5, 1) X(6, 1) X(7, 1) X(8, 1) X(10, 1) X(12, 1) X(16, 1) \
-    X(20, 1) X(24, 1) X(32, 1) X(8, 8) X(8, 16) X(8, 32) X(16, 32) X(32, 32)
+    X(20, 1) X(24, 1) X(32, 1) X(24, 2) X(32, 2) X(24, 4) X(32, 4) X(20, 8) X(24, 8) X(32, 8)  \
+    X(24, 16) X(32, 16) X(24, 32) X(32, 32)
 
 // BitPAl packed
 #define BGSA_BITPAL_PACKED_INSTANCES(X)                                                      \
-    X(1, 1) X(2, 1) X(3, 1) X(4, 1) X(5, 1) X(6, 1) X(4, 2) X(6, 2) X(4, 4) X(6, 4) X(4, 8)   \
-    X(6, 8) X(4, 16) X(6, 16) X(4, 32) X(5, 32) X(6, 32) X(8, 32)
+    X(1, 1) X(2, 1) X(3, 1) X(4, 1) X(5, 1) X(6, 1) X(8, 1) X(10, 1) X(6, 2) X(8, 2) X(10, 2)  \
+    X(6, 4) X(8, 4) X(10, 4) X(6, 8) X(8, 8) X(10, 8) X(6, 16) X(8, 16) X(10, 16) X(5, 32)     \
+    X(6, 32) X(8, 32) X(10, 32)
 
 // BitPAl non-packed (one vector per delta value: register hungry, so few words per lane)
 #define BGSA_BITPAL_NONPACKED_INSTANCES(X)                                                   \

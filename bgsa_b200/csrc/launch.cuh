@@ -40,7 +40,7 @@ cudaError_t launch_align(const LaunchArgs &a, typename Algo::Params prm) {
     cudaError_t e = cudaMemsetAsync(a.d_counters, 0, sizeof(unsigned long long) * a.n_queries, a.stream);
     if (e != cudaSuccess) return e;
     const long long warps_per_cta = kAlignThreads / 32;
-    long long want = (a.ps.ntiles + warps_per_cta - 1) / warps_per_cta;       // one tile per warp at least
+    long long want = (a.ps.ntiles * L + warps_per_cta - 1) / warps_per_cta;   // one (tile, pass) work unit per warp at least
     long long resident = (long long)a.sm_count * occ / (a.n_queries > 0 ? a.n_queries : 1);
     if (resident < 1) resident = 1;
     if (want > resident) want = resident;

@@ -30,8 +30,8 @@ struct MyersAlgo {
     static constexpr int K = K_;
     using Params = MyersParams;
     struct State { uint32_t pv[K], mv[K]; };
-    // carry word layout: bit 3 add carry, bit 4 Ph shift-in, bit 5 Mh shift-in
-    static constexpr uint32_t kBoundary = 1u << 4;   // top row: D[0][i] - D[0][i-1] = +1
+    // carry stream (CarryIn/CarryOut, consumption order): add carry, Ph shift-in, Mh shift-in
+    static constexpr uint32_t kBoundary = 0x40000000u;   // top row: no carry, D[0][i] - D[0][i-1] = +1 (Ph), Mh 0
 
     static BGSA_HD void init(State &s) {
 #pragma unroll
@@ -47,9 +47,10 @@ struct MyersAlgo {
             const uint4 v = reinterpret_cast<const uint4 *>(row)[j];
             eq[4 * j] = v.x; eq[4 * j + 1] = v.y; eq[4 * j + 2] = v.z; eq[4 * j + 3] = v.w;
         }
-        uint32_t ph_prev = CARRY ? (cin << 27) : 0x80000000u;   // only bit 31 is consumed
-        uint32_t mh_prev = CARRY ? (cin << 26) : 0u;
-        if (CARRY) (void)add_cc(cin & 8u, 0xffffffffu);          // CF := add carry from the lane above
+        CarryIn in(cin);
+        if (CARRY) in.to_cf();                                   // CF := add carry from the lane above
+        uint32_t ph_prev = CARRY ? in.top() : 0x80000000u;       // only bit 31 is consumed
+        uint32_t mh_prev = CARRY ? in.top() : 0u;
 #pragma unroll
         for (int j = 0; j < K; j++) {
             const uint32_t p = s.pv[j], m = s.mv[j], e = eq[j];
@@ -66,8 +67,11 @@ struct MyersAlgo {
             s.mv[j] = phs & d0;
         }
         if (!CARRY) return 0u;
-        const uint32_t cout = addc(0u, 0u);
-        return (cout << 3) | ((ph_prev >> 31) << 4) | ((mh_prev >> 31) << 5);
+        CarryOut out;
+        out.push_cf();
+        out.push_top(ph_prev);
+        out.push_top(mh_prev);
+        return out.finish<3>();
     }
 
     // pieces of the final vertical delta vector held by this lane (bits first_bit .. first_bit+32K)

@@ -83,7 +83,7 @@ def test_no_cpu_fallback_and_error_codes():
 def test_kernel_selection_matches_baseline_configs():
     import bgsa_b200 as B
     assert B.kernel_name(B.Params.default(B.BITPAL_PACKED), 150, 150) == "align_kernel<BitpalPacked<2,-3,-5,K=5>,L=1>"
-    assert B.kernel_name(B.Params.default(B.BITPAL_PACKED), 5000, 5000) == "align_kernel<BitpalPacked<2,-3,-5,K=5>,L=32>"
+    assert B.kernel_name(B.Params.default(B.BITPAL_PACKED), 5000, 5000) == "align_kernel<BitpalPacked<2,-3,-5,K=10>,L=16>"
     assert B.kernel_name(B.Params.default(B.MYERS_SEMIGLOBAL), 1000, 1000) == "align_kernel<MyersAlgo<K=32,semiglobal>,L=1>"
     assert B.kernel_name(B.Params.default(B.MYERS_GLOBAL), 500, 500) == "align_kernel<MyersAlgo<K=16,global>,L=1>"
     assert B.kernel_name(B.Params.default(B.BANDED_MYERS, threshold=5), 100, 100) == "banded_kernel<u32>"
