@@ -5,7 +5,7 @@ GCC      ?= gcc
 ARCH     := -gencode arch=compute_100a,code=sm_100a
 # EXTRA: additional nvcc flags for experiment builds, e.g. make lib BUILD=build/x LIB=bgsa_b200/libx.so EXTRA=-DBGSA_FMA_SHIFT=0
 EXTRA    ?=
-NVFLAGS  := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -Wall -Xcompiler -Wno-unused-function $(EXTRA)
+NVFLAGS  := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -Wall -Xcompiler -Wno-unused-function -Xcompiler -Wno-unknown-pragmas $(EXTRA)
 CSRC     := bgsa_b200/csrc
 HOST     := bgsa_b200/host
 BUILD    ?= build

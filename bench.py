@@ -29,6 +29,7 @@ import subprocess
 import sys
 import threading
 import time
+import zlib
 from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent
@@ -122,13 +123,13 @@ def reference_run(wl: dict, query, subjects, min_seconds: float, max_runs: int):
     t_handle, t_cal, runs = [], [], 0
     t_begin = time.perf_counter()
     while runs < max_runs and (runs < 2 or time.perf_counter() - t_begin < min_seconds):
-        t0 = time.perf_counter(); ref.handle_reads(st); t1 = time.perf_counter(); ref.cal_align_score(st); t2 = time.perf_counter()
+        t0 = time.perf_counter(); ref.handle_reads(st); t1 = time.perf_counter(); scores = ref.cal_align_score(st); t2 = time.perf_counter()
         t_handle.append(t1 - t0); t_cal.append(t2 - t1); runs += 1
     cells = float(query.shape[1] - 1) * (subjects.shape[1] - 1) * subjects.shape[0] * query.shape[0]
     th, tc = min(t_handle), min(t_cal)
     kind = "port" if variant == "semiglobal_cpu" else "reference"
     return dict(variant=variant, kind=kind, cores=ref.threads, runs=runs, cells=cells, t_handle=th, t_cal=tc,
-                gcups_path=cells / (th + tc) / 1e9, gcups_cal=cells / tc / 1e9)
+                gcups_path=cells / (th + tc) / 1e9, gcups_cal=cells / tc / 1e9, scores=scores)
 
 
 def main():
@@ -315,9 +316,12 @@ def main():
                                     "variant": res["variant"], "cal_only_gcups": res["gcups_cal"],
                                     "sample": f"{min(ns, 1_000_000)} subjects of the same workload, best of {res['runs']} runs, "
                                               f"Peq build ({res['t_handle']:.3f} s) + kernel ({res['t_cal']:.3f} s)"}
-        else:
-            line["cpu_baseline"] = {"value": None, "unit": "GCUPS", "cores": os.cpu_count(), "kind": "reference",
-                                    "sample": "oracle/_ref not usable on this host CPU"}
+            # the checker at work: the scores the timed e2e steps left in the pinned result buffer against the
+            # reference's scores for the same subjects (bit-exact or the run is worthless)
+            nref = res["scores"].shape[1]
+            mism = int((out_pinned[:, :nref] != res["scores"]).sum())
+            line["parity"] = {"against": res["variant"], "subjects_compared": int(nref), "mismatches": mism,
+                              "crc32_all_scores": "%08x" % zlib.crc32(out_pinned.tobytes())}
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

@@ -71,14 +71,18 @@ align_kernel(PackedSubjects ps, const uint32_t *__restrict__ g_peq, int qlen, in
     const int slen = ps.slen, ku = ps.ku;
     const int nstages = (ku + CH - 1) / CH;
 
-    // work unit = (tile, pass): the 32/L subjects of a tile that a warp has in flight at once
+    // work unit = (tile, pass): the 32/L subjects of a tile that a warp has in flight at once.  Every warp starts
+    // on "its own" unit (static), further units come from the global counter: the next unit is claimed one unit
+    // ahead (its first stage is prefetched), and with a purely dynamic start the first warps to arrive would claim
+    // two units each while others get none whenever a launch holds about one unit per warp (chunked batches).
     const long long nunits = ps.ntiles * L;
-    long long unit = next_tile(counter, lane);
+    const long long total_warps = (long long)gridDim.x * WARPS;
+    long long unit = (long long)blockIdx.x * WARPS + warp;
     int sb = 0;
     if (unit < nunits) st.issue(0, ps.codes + (unit / L) * ku * 32, min(CH, ku), lane);
 
     while (unit < nunits) {
-        const long long nxt = next_tile(counter, lane);
+        const long long nxt = total_warps + next_tile(counter, lane);
         const long long tile = unit / L;
         const int pass = (int)(unit % L);
         const bool with_n = ps.tile_has_n[tile] != 0;

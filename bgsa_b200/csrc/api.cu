@@ -160,10 +160,15 @@ constexpr int kLanesPerJob = 3;
 // A "job" = one bgsa_align_batch_submit() call: the subject range is cut into chunks that
 // rotate over the job's lanes.  Two jobs (slot 0 / 1) can be in flight per device, mirroring the
 // reference's a/b ping-pong buffers (cal_cpu.c:258-267, thread.c:35-170).
+// BGSA_TRACE=1: per-chunk device timeline (ms since submit) printed to stderr by bgsa_align_batch_wait --
+// the GPU-side counterpart of the reference's read/mem/cal/write timers (cal_cpu.c:459-475).
+struct ChunkTrace { int64_t off, n; int lane; cudaEvent_t ev[4]; };     // after H2D, pack, align, D2H
 struct Job {
     Lane lane[kLanesPerJob];
     QueryCache qc;
     cudaEvent_t tab_ready = nullptr;
+    cudaEvent_t t0 = nullptr;            // trace origin
+    std::vector<ChunkTrace> trace;
 };
 struct DeviceCtx {
     bool ready = false;
@@ -382,24 +387,38 @@ int bgsa_align_batch_submit(const bgsa_params_t *p, const char *queries, int n_q
     rc = stage_queries(job.qc, plan, queries, n_queries, query_len, slen, job.lane[0].stream, &d_tab);
     if (rc) return rc;
     CUDA_TRY(cudaEventRecord(job.tab_ready, job.lane[0].stream));
-    // chunking: tile-aligned, at most ~8 chunks, never below 32 Ki subjects (launch overheads)
-    // Chunking.  The persistent grid works on `quantum` subjects at once (resident warps x subjects per warp); a
-    // chunk that is a whole number of quanta keeps every warp busy for the same number of rounds, anything else
-    // leaves part of the GPU idle for a round.  Aim at ~6 chunks (enough to hide the H2D of all but the first).
+    // Chunking.  The persistent grid works on `quantum` subjects at once (resident warps x subjects per warp) and
+    // every warp starts on its own work unit, so a chunk of a whole number of quanta keeps all warps busy for the
+    // same number of rounds.  Small chunks let the kernels follow the H2D stream closely (only the first chunk's
+    // copy and the last chunk's kernel are exposed): aim at ~16 chunks, never below one quantum or 4 MB of rows.
     long long quantum = 0;
     rc = run_align(plan, ctx->sm_count, d_tab, nullptr, n_queries, query_len, nullptr, slen, 0, nullptr, 0, nullptr, &quantum);
     if (rc) return rc;
     if (quantum < kTileSubjects) quantum = kTileSubjects;
-    static const int kChunks = getenv("BGSA_CHUNKS") ? atoi(getenv("BGSA_CHUNKS")) : 6;   // tuning knob
+    static const int kChunks = getenv("BGSA_CHUNKS") ? atoi(getenv("BGSA_CHUNKS")) : 16;   // tuning knob
+    static const bool kTrace = getenv("BGSA_TRACE") != nullptr;
+    const int64_t min_subjects = ((4 << 20) + slen) / (slen + 1);
+    int64_t min_rounds = (min_subjects + quantum - 1) / quantum;
+    if (min_rounds < 1) min_rounds = 1;
     int64_t rounds = (count / (kChunks > 0 ? kChunks : 1) + quantum / 2) / quantum;
-    if (rounds < 1) rounds = 1;
-    int64_t chunk = rounds * quantum;
-    if (chunk < 32768) chunk = (32768 + quantum - 1) / quantum * quantum;
-    chunk = (chunk + kTileSubjects - 1) / kTileSubjects * kTileSubjects;
+    if (rounds < min_rounds) rounds = min_rounds;
+    const int64_t chunk = (rounds * quantum + kTileSubjects - 1) / kTileSubjects * kTileSubjects;
+    int64_t first_chunk = (min_rounds * quantum + kTileSubjects - 1) / kTileSubjects * kTileSubjects;
+    if (count < 2 * chunk) first_chunk = chunk;
+    if (kTrace) {
+        if (!job.t0) CUDA_TRY(cudaEventCreate(&job.t0));
+        for (ChunkTrace &c : job.trace) for (cudaEvent_t e : c.ev) cudaEventDestroy(e);
+        job.trace.clear();
+        CUDA_TRY(cudaEventRecord(job.t0, job.lane[0].stream));
+    }
     int li = 0;
-    for (int64_t off = 0; off < count; off += chunk, li = (li + 1) % kLanesPerJob) {
-        const int64_t n = count - off < chunk ? count - off : chunk;
+    for (int64_t off = 0, step = first_chunk; off < count; off += step, step = chunk, li = (li + 1) % kLanesPerJob) {
+        const int64_t n = count - off < step ? count - off : step;
         Lane &l = job.lane[li];
+        ChunkTrace tr{off, n, li, {nullptr, nullptr, nullptr, nullptr}};
+        auto mark = [&](int i) {
+            if (kTrace && cudaEventCreate(&tr.ev[i]) == cudaSuccess) cudaEventRecord(tr.ev[i], l.stream);
+        };
         const size_t row_bytes = (size_t)n * (slen + 1);
         if ((rc = l.d_rows.ensure(row_bytes + 16))) return rc;
         if ((rc = l.d_packed.ensure((size_t)packed_bytes(slen, n)))) return rc;
@@ -408,16 +427,21 @@ int bgsa_align_batch_submit(const bgsa_params_t *p, const char *queries, int n_q
         // host -> device: the ASCII rows exactly as file.c:44-115 left them
         CUDA_TRY(cudaMemcpyAsync(l.d_rows.p, subjects->content + (size_t)(first + off) * (slen + 1), row_bytes,
                                  cudaMemcpyHostToDevice, l.stream));
+        mark(0);
         cudaError_t e = launch_pack(plan.layout, l.d_rows.p, slen, n, l.d_packed.p, ctx->sm_count, l.stream);
         if (e != cudaSuccess) return fail(BGSA_ERR_CUDA, "pack kernel launch failed: %s", cudaGetErrorString(e));
         g_launches.fetch_add(1);
+        mark(1);
         if (li != 0) CUDA_TRY(cudaStreamWaitEvent(l.stream, job.tab_ready, 0));
         rc = run_align(plan, ctx->sm_count, d_tab, static_cast<unsigned long long *>(l.d_counters.p), n_queries, query_len,
                        l.d_packed.p, slen, n, l.d_results.p, n, l.stream);
         if (rc) return rc;
+        mark(2);
         // device -> host: [query][subject] rows into the caller's (possibly wider) result matrix
         CUDA_TRY(cudaMemcpy2DAsync(static_cast<char *>(results) + esize * (size_t)off, esize * (size_t)result_stride, l.d_results.p,
                                    esize * (size_t)n, esize * (size_t)n, (size_t)n_queries, cudaMemcpyDeviceToHost, l.stream));
+        mark(3);
+        if (kTrace) job.trace.push_back(tr);
     }
     return BGSA_OK;
 }
@@ -427,7 +451,21 @@ int bgsa_align_batch_wait(int device, int slot) {
     DeviceCtx *ctx;
     int rc = get_ctx(device, &ctx);
     if (rc) return rc;
-    for (Lane &l : ctx->job[slot].lane) CUDA_TRY(cudaStreamSynchronize(l.stream));
+    Job &job = ctx->job[slot];
+    for (Lane &l : job.lane) CUDA_TRY(cudaStreamSynchronize(l.stream));
+    if (!job.trace.empty()) {
+        fprintf(stderr, "[bgsa trace] device %d slot %d: chunk(first,count,lane)  h2d_done pack_done align_done d2h_done [ms since submit]\n",
+                device, slot);
+        for (ChunkTrace &c : job.trace) {
+            float t[4] = {-1.f, -1.f, -1.f, -1.f};
+            for (int i = 0; i < 4; i++) {
+                if (c.ev[i]) { cudaEventElapsedTime(&t[i], job.t0, c.ev[i]); cudaEventDestroy(c.ev[i]); }
+            }
+            fprintf(stderr, "[bgsa trace]   %10lld %9lld %d   %8.3f %8.3f %8.3f %8.3f\n", (long long)c.off, (long long)c.n, c.lane,
+                    t[0], t[1], t[2], t[3]);
+        }
+        job.trace.clear();
+    }
     return BGSA_OK;
 }
 

@@ -161,15 +161,20 @@ __device__ __noinline__ uint2 encode_piece_exact(const uint4 v) {
 // CODES : base i at bits 2i.   PLANES: low code bit of base i at bit i, high code bit at bit 16+i.
 template <int LAYOUT>
 __device__ __forceinline__ uint32_t encode_piece(const uint4 v, int e, uint32_t &cw) {
-    const uint32_t c06 = 0x06060606u, c40 = 0x40404040u, cE8 = 0xE8E8E8E8u, c10 = 0x10101010u;
+    const uint32_t c40 = 0x40404040u, cE8 = 0xE8E8E8E8u, c10 = 0x10101010u;
     const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-    uint32_t x[4], accbad = 0u;
+    uint32_t x[4], xh[4], accbad = 0u;
 #pragma unroll
     for (int j = 0; j < 4; j++) {
         // Left shifts only where possible: they compile to IMAD.SHL (FMA pipe), the ALU pipe is this kernel's bound.
-        // code bits land at bits 1-2 of every byte, the two validity tests at bit 4.
+        // code bits (b1^b2, b2^b3) land at bits 1-2 of every byte, the two validity tests at bit 4.
         const uint32_t s1 = w[j] >> 1, l2 = w[j] << 2, l3 = w[j] << 3, l4 = w[j] << 4;
-        x[j] = lop3<(LA ^ LB) & LC>(w[j], s1, c06);                          // (b1^b2, b2^b3) = code
+        if (LAYOUT == LAYOUT_CODES) {
+            x[j] = lop3<(LA ^ LB) & LC>(w[j], s1, 0x06060606u);
+        } else {
+            x[j] = lop3<(LA ^ LB) & LC>(w[j], s1, 0x02020202u);              // low code bit
+            xh[j] = lop3<(LA ^ LB) & LC>(w[j], s1, 0x04040404u);             // high code bit
+        }
         const uint32_t v2 = lop3<LA ^ ((0xFF ^ LB) | LC)>(w[j], l2, l3);     // bit 4: b4 ^ (~b2 | b1)
         const uint32_t g = lop3<(LA ^ LB) & LC>(w[j], l4, v2);               // bit 4: (b4 ^ b0) & v2
         uint32_t bad = lop3<(LA ^ LB) & LC>(w[j], c40, cE8);                 // (b & 0xE8) != 0x40
@@ -177,19 +182,17 @@ __device__ __forceinline__ uint32_t encode_piece(const uint4 v, int e, uint32_t 
         const uint32_t excuse = shl_clamp(0xffu, (uint32_t)(8 * e - 32 * j));     // the row-end byte may be anything
         accbad = lop3<LA | (LB & (0xFF ^ LC))>(accbad, bad, excuse);
     }
+    // Gather by integer multiply (FMA pipe): the partial products of the chosen constants never overlap, the
+    // wanted bits end up in the top byte; PRMT merges the top bytes.
     if (LAYOUT == LAYOUT_CODES) {
-        const uint32_t K = (1u << 23) | (1u << 17) | (1u << 11) | (1u << 5);
+        const uint32_t K = (1u << 23) | (1u << 17) | (1u << 11) | (1u << 5);         // 4 x 2 bits of one word
         const uint32_t t01 = prmt(x[0] * K, x[1] * K, 0x0073u), t23 = prmt(x[2] * K, x[3] * K, 0x0073u);
         cw = prmt(t01, t23, 0x5410u);
     } else {
-        const uint32_t KL = (1u << 27) | (1u << 20) | (1u << 13) | (1u << 6);
-        uint32_t lo = 0u, hi = 0u;
-#pragma unroll
-        for (int j = 3; j >= 0; j--) {
-            lo = __funnelshift_l((x[j] & 0x02020202u) * KL, lo, 4);
-            hi = __funnelshift_l((x[j] & 0x04040404u) * (KL >> 1), hi, 4);
-        }
-        cw = lo | (hi << 16);
+        const uint32_t KP = (1u << 23) | (1u << 16) | (1u << 9) | (1u << 2);         // 8 x 1 bit of two words (second << 4)
+        const uint32_t lo01 = (x[1] * 16u + x[0]) * KP, lo23 = (x[3] * 16u + x[2]) * KP;
+        const uint32_t hi01 = (xh[1] * 16u + xh[0]) * (KP >> 1), hi23 = (xh[3] * 16u + xh[2]) * (KP >> 1);
+        cw = prmt(prmt(lo01, lo23, 0x0073u), prmt(hi01, hi23, 0x0073u), 0x5410u);    // lo16 | hi16 << 16
     }
     return accbad;
 }
@@ -216,29 +219,27 @@ pack_stream_kernel(const uint8_t *__restrict__ rows, int slen, long long count, 
         const int live_rows = (int)min((long long)kTileSubjects, count - first);
         const uint4 *src = reinterpret_cast<const uint4 *>(rows + first * stride - off);
         const int npieces = (off + live_rows * stride + 15) >> 4;
-        // ---- step 1: stream order
+        // ---- step 1: stream order.  Whole groups of kPackUnroll x 32 pieces first (no bounds checks, loads in
+        // flight before the first is used), then the remainder one piece per lane and trip.
         uint32_t any_n = 0u;
         int m = m0;
-        for (int p0 = lane; p0 < npieces; p0 += 32 * kPackUnroll) {
+        const int full = npieces - npieces % (32 * kPackUnroll);
+        int p0 = lane;
+        for (; p0 < full; p0 += 32 * kPackUnroll) {
             uint4 v[kPackUnroll];
 #pragma unroll
-            for (int k = 0; k < kPackUnroll; k++) {
-                const int p = p0 + 32 * k;
-                v[k] = p < npieces ? __ldg(src + p) : make_uint4(0x41414141u, 0x41414141u, 0x41414141u, 0x41414141u);
-            }
+            for (int k = 0; k < kPackUnroll; k++) v[k] = __ldg(src + p0 + 32 * k);
+            const int ph = pack_phys(p0);                           // pack_phys(p0 + 32k) = ph + 33k
             uint32_t redo = 0u;                                     // bit k: piece k needs the exact path
 #pragma unroll
             for (int k = 0; k < kPackUnroll; k++) {
-                const int p = p0 + 32 * k;
                 uint32_t cw;
                 const uint32_t bad = encode_piece<LAYOUT>(v[k], slen - m, cw);
                 m += inc;
                 if (m >= stride) m -= stride;
-                if (p < npieces) {
-                    s_c[pack_phys(p)] = cw;
-                    s_n[p] = (uint16_t)0;
-                    redo |= (bad != 0u ? 1u : 0u) << k;
-                }
+                s_c[ph + 33 * k] = cw;
+                s_n[p0 + 32 * k] = (uint16_t)0;
+                redo |= (bad != 0u ? 1u : 0u) << k;
             }
             while (redo) {                                          // rare: 'N', lower case, ...
                 const int k = __ffs(redo) - 1;
@@ -249,6 +250,24 @@ pack_stream_kernel(const uint8_t *__restrict__ rows, int slen, long long count, 
                 s_n[p] = (uint16_t)r.y;
                 any_n |= r.y;
             }
+        }
+        uint32_t redo_tail = 0u;                                    // bit i: tail piece p0 + 32 i needs the exact path
+        for (int p = p0, i = 0; p < npieces; p += 32, i++) {
+            uint32_t cw;
+            const uint32_t bad = encode_piece<LAYOUT>(__ldg(src + p), slen - m, cw);
+            m += inc;
+            if (m >= stride) m -= stride;
+            s_c[pack_phys(p)] = cw;
+            s_n[p] = (uint16_t)0;
+            redo_tail |= (bad != 0u ? 1u : 0u) << i;
+        }
+        while (redo_tail) {
+            const int p = p0 + 32 * (__ffs(redo_tail) - 1);
+            redo_tail &= redo_tail - 1u;
+            const uint2 r = encode_piece_exact<LAYOUT>(__ldg(src + p));
+            s_c[pack_phys(p)] = r.x;
+            s_n[p] = (uint16_t)r.y;
+            any_n |= r.y;
         }
         const bool tile_n = __ballot_sync(0xffffffffu, any_n != 0u) != 0u;
         __syncwarp();

@@ -26,4 +26,4 @@ d = torch.empty_like(h, device="cuda")
 torch.cuda.synchronize(); t1 = time.perf_counter()
 for _ in range(5): d.copy_(h, non_blocking=True)
 torch.cuda.synchronize(); th = (time.perf_counter() - t1) / 5
-print(f"{name} chunks={os.environ.get('BGSA_CHUNKS','8')} e2e {t*1e3:.3f} ms -> {cells/t/1e9:.0f} GCUPS ; raw H2D {th*1e3:.3f} ms ({h.numel()/th/1e9:.1f} GB/s)")
+print(f"{name} chunks={os.environ.get("BGSA_CHUNKS","default")} e2e {t*1e3:.3f} ms -> {cells/t/1e9:.0f} GCUPS ; raw H2D {th*1e3:.3f} ms ({h.numel()/th/1e9:.1f} GB/s)")
