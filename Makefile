@@ -54,11 +54,15 @@ tests/libhost_sim.so: tests/host_sim.cu $(HDRS)
 SHIMS := myers_cpu semiglobal_cpu banded_cpu myers_sse bitpal_avx2 bitpal_avx512
 SHIM_LIBS := $(foreach v,$(SHIMS),bgsa_b200/libalign_core_$(v).so)
 
-tools: bgsa_b200/aligner $(SHIM_LIBS)
+tools: bgsa_b200/aligner bgsa_b200/convert $(SHIM_LIBS)
 
 # host code is plain C (gcc); it reaches CUDA only through the C ABI of libbgsa_b200.so
 bgsa_b200/aligner: $(HOST)/aligner.c include/bgsa_b200.h $(LIB)
 	$(GCC) -O2 -Wall -o $@ $(HOST)/aligner.c -Lbgsa_b200 -lbgsa_b200 -Wl,-rpath,'$$ORIGIN'
+
+# no GPU code: FASTA/FASTQ -> line format, result file -> text (the reference's convert tool)
+bgsa_b200/convert: $(HOST)/convert.c
+	$(GCC) -O2 -Wall -o $@ $(HOST)/convert.c
 
 upper = $(shell echo $(1) | tr a-z A-Z)
 bgsa_b200/libalign_core_%.so: $(HOST)/align_core_shim.c include/align_core.h include/bgsa_b200.h $(LIB)
@@ -68,4 +72,4 @@ $(BUILD):
 	mkdir -p $(BUILD)
 
 clean:
-	rm -rf $(BUILD) $(LIB) tests/libhost_sim.so bgsa_b200/aligner $(SHIM_LIBS)
+	rm -rf $(BUILD) $(LIB) tests/libhost_sim.so bgsa_b200/aligner bgsa_b200/convert $(SHIM_LIBS)

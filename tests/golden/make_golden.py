@@ -37,6 +37,10 @@ def main():
     per_dev = raw.reshape(2, 3, 64)
     np.savez_compressed(HERE / "golden_semiglobal_knc.npz", scores=np.concatenate([per_dev[0], per_dev[1]], axis=1),
                         raw=raw, info=np.frombuffer(info, dtype=np.uint8))
+    # the same golden as files, plus the text the reference's own convert made of it (tests/test_convert_tool.py)
+    shutil.copy(REF / "banded/BGSA_KNC/data/result.txt", HERE / "knc_result.bin")
+    shutil.copy(REF / "banded/BGSA_KNC/data/result.txt.info", HERE / "knc_result.bin.info")
+    shutil.copy(REF / "banded/BGSA_KNC/data/convert_result.txt", HERE / "knc_convert_result.txt")
 
     out = {}
     q, s = R.sample_data()

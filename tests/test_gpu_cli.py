@@ -170,3 +170,23 @@ def test_reference_pipeline_semiglobal_and_banded_dropin(sample, tmp_path, golde
                    cwd=tmp_path, env=env, check=True, stdout=subprocess.DEVNULL, timeout=600)
     got = np.fromfile(tmp_path / "d_banded.bin", dtype=np.int8)
     assert (got[None, :] == R.oracle_batch(R.ALGO_BANDED, q, s, e=5)).all()
+
+
+def test_fasta_to_scores_with_our_convert_tool(tmp_path):
+    """The whole tool chain of the reference README: convert -f / -q, aligner, convert -r -- all ours."""
+    convert = ROOT / "bgsa_b200" / "convert"
+    assert convert.exists(), "bgsa_b200/convert not built (make tools)"
+    rng = np.random.default_rng(8)
+    q = R.random_rows(rng, 2, 120)
+    s = np.concatenate([R.mutate_rows(rng, q[0, :120], 300, 10), R.random_rows(rng, 212, 120, with_n=0.01)])
+    fasta = "".join(f">s{i} x\n{bytes(r[:70]).decode()}\n{bytes(r[70:120]).decode()}\n" for i, r in enumerate(s))
+    fastq = "".join(f"@q{i}\n{bytes(r[:120]).decode()}\n+\n{'I' * 120}\n" for i, r in enumerate(q))
+    (tmp_path / "s.fa").write_text(fasta); (tmp_path / "q.fq").write_text(fastq)
+    run([convert, "-f", "s.fa", "-o", "s.txt"], tmp_path)
+    run([convert, "-q", "q.fq", "-o", "q.txt"], tmp_path)
+    assert (tmp_path / "s.txt").read_bytes() == s.tobytes() and (tmp_path / "q.txt").read_bytes() == q.tobytes()
+    for algo, oalgo, bytes_per, extra in (("bitpal", R.ALGO_BITPAL_PACKED, "2", []), ("banded", R.ALGO_BANDED, "1", ["-k", "7"])):
+        run([ALIGNER, "-a", algo, "-q", "q.txt", "-d", "s.txt", "-f", "r.bin", "-g", "1"] + extra, tmp_path)
+        run([convert, "-r", "r.bin", "-o", "r.txt", "-b", bytes_per], tmp_path)
+        got = np.array((tmp_path / "r.txt").read_text().split(), dtype=np.int64).reshape(2, -1)
+        assert (got == R.oracle_batch(oalgo, q, s, e=7)).all()
