@@ -15,7 +15,8 @@ HDRS := $(wildcard $(CSRC)/*.cuh $(CSRC)/*.h) include/bgsa_b200.h
 
 OBJS := $(BUILD)/api.o $(BUILD)/inst_misc.o $(BUILD)/inst_myers_g.o $(BUILD)/inst_myers_s.o \
         $(BUILD)/inst_bp_p0.o $(BUILD)/inst_bp_p1.o $(BUILD)/inst_bp_p2.o \
-        $(BUILD)/inst_bp_n0.o $(BUILD)/inst_bp_n1.o $(BUILD)/inst_bp_n2.o
+        $(BUILD)/inst_bp_n0.o $(BUILD)/inst_bp_n1.o $(BUILD)/inst_bp_n2.o \
+        $(BUILD)/inst_bp_s0.o $(BUILD)/inst_bp_s1.o $(BUILD)/inst_bp_s2.o
 
 .PHONY: all lib tools sim clean
 all: lib tools sim
@@ -32,7 +33,7 @@ $(BUILD)/inst_myers_g.o: $(CSRC)/inst_myers.cu $(HDRS) | $(BUILD)
 	$(NVCC) $(NVFLAGS) -DBGSA_MYERS_MODE=0 -c $< -o $@
 $(BUILD)/inst_myers_s.o: $(CSRC)/inst_myers.cu $(HDRS) | $(BUILD)
 	$(NVCC) $(NVFLAGS) -DBGSA_MYERS_MODE=1 -c $< -o $@
-# BitPAl: one object per (scheme id, packed?) -- keep in sync with BGSA_SCHEMES in instances.h
+# BitPAl: one object per (scheme id, variant: p packed, n non-packed, s packed semi-global) -- keep in sync with BGSA_SCHEMES in instances.h
 $(BUILD)/inst_bp_p0.o: $(CSRC)/inst_bitpal.cu $(HDRS) | $(BUILD)
 	$(NVCC) $(NVFLAGS) -DBGSA_SCHEME_ID=0 -DBGSA_M=2 -DBGSA_I=-3 -DBGSA_G=-5 -DBGSA_PACKED=1 -c $< -o $@
 $(BUILD)/inst_bp_p1.o: $(CSRC)/inst_bitpal.cu $(HDRS) | $(BUILD)
@@ -45,6 +46,13 @@ $(BUILD)/inst_bp_n1.o: $(CSRC)/inst_bitpal.cu $(HDRS) | $(BUILD)
 	$(NVCC) $(NVFLAGS) -DBGSA_SCHEME_ID=1 -DBGSA_M=1 -DBGSA_I=-1 -DBGSA_G=-1 -DBGSA_PACKED=0 -c $< -o $@
 $(BUILD)/inst_bp_n2.o: $(CSRC)/inst_bitpal.cu $(HDRS) | $(BUILD)
 	$(NVCC) $(NVFLAGS) -DBGSA_SCHEME_ID=2 -DBGSA_M=1 -DBGSA_I=-3 -DBGSA_G=-2 -DBGSA_PACKED=0 -c $< -o $@
+
+$(BUILD)/inst_bp_s0.o: $(CSRC)/inst_bitpal.cu $(HDRS) | $(BUILD)
+	$(NVCC) $(NVFLAGS) -DBGSA_SCHEME_ID=0 -DBGSA_M=2 -DBGSA_I=-3 -DBGSA_G=-5 -DBGSA_PACKED=2 -c $< -o $@
+$(BUILD)/inst_bp_s1.o: $(CSRC)/inst_bitpal.cu $(HDRS) | $(BUILD)
+	$(NVCC) $(NVFLAGS) -DBGSA_SCHEME_ID=1 -DBGSA_M=1 -DBGSA_I=-1 -DBGSA_G=-1 -DBGSA_PACKED=2 -c $< -o $@
+$(BUILD)/inst_bp_s2.o: $(CSRC)/inst_bitpal.cu $(HDRS) | $(BUILD)
+	$(NVCC) $(NVFLAGS) -DBGSA_SCHEME_ID=2 -DBGSA_M=1 -DBGSA_I=-3 -DBGSA_G=-2 -DBGSA_PACKED=2 -c $< -o $@
 
 # test-only: the DP column functions compiled for the HOST (no GPU needed), see tests/host_sim.cu
 sim: tests/libhost_sim.so

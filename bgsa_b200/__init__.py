@@ -20,12 +20,12 @@ from pathlib import Path
 import numpy as np
 
 __all__ = [
-    "MYERS_GLOBAL", "MYERS_SEMIGLOBAL", "BANDED_MYERS", "BITPAL_PACKED", "BITPAL_NONPACKED",
+    "MYERS_GLOBAL", "MYERS_SEMIGLOBAL", "BANDED_MYERS", "BITPAL_PACKED", "BITPAL_NONPACKED", "BITPAL_PACKED_SEMIGLOBAL",
     "BgsaError", "Params", "SeqT", "load", "lib_path", "align_batch", "result_dtype", "to_codes",
     "packed_bytes", "pack_subjects_device", "align_device", "int_peak", "launch_count", "kernel_name", "supported",
 ]
 
-MYERS_GLOBAL, MYERS_SEMIGLOBAL, BANDED_MYERS, BITPAL_PACKED, BITPAL_NONPACKED = range(5)
+MYERS_GLOBAL, MYERS_SEMIGLOBAL, BANDED_MYERS, BITPAL_PACKED, BITPAL_NONPACKED, BITPAL_PACKED_SEMIGLOBAL = range(6)
 _STATUS = {1: "BGSA_ERR_ARG", 2: "BGSA_ERR_UNSUPPORTED", 3: "BGSA_ERR_CUDA", 4: "BGSA_ERR_NOMEM"}
 
 

@@ -4,7 +4,7 @@
 // An algorithm is a policy class:
 //     static constexpr int K;                         // 32-bit words of the bit-vector PER LANE
 //     struct State;  struct Params;                   // per-lane DP state (registers), constants
-//     static void init(State&);
+//     static void init(State&, int first_bit, int qlen);   // first_bit: where this lane's segment starts
 //     template <bool CARRY> static uint32_t column(State&, const uint32_t* peq_row, uint32_t cin);
 //         one DP column = one subject base.  With CARRY the low word's carry-ins come from `cin`
 //         (a CarryIn stream, top-aligned, bits 0..2 ignored) and the carry-outs are returned as
@@ -89,7 +89,7 @@ align_kernel(PackedSubjects ps, const uint32_t *__restrict__ g_peq, int qlen, in
         {
             const int sidx = pass * GROUPS + group;          // subject of this group inside the tile
             typename Algo::State state;
-            Algo::init(state);
+            Algo::init(state, rank * K * 32, qlen);
             uint32_t packet = 0u;                            // what this lane hands to lane rank+1
             int t = 0;                                       // wavefront step = column of lane 0 (checked steps only)
 

@@ -104,12 +104,13 @@ int make_plan(const bgsa_params_t *p, int qlen, int slen, Plan *plan) {
                 return fail(BGSA_ERR_UNSUPPORTED, "Myers: query length %d exceeds the largest kernel instance (32768)", qlen);
             return BGSA_OK;
         case BGSA_BITPAL_PACKED:
+        case BGSA_BITPAL_PACKED_SEMIGLOBAL:
         case BGSA_BITPAL_NONPACKED: {
             plan->scheme = find_scheme(p->match, p->mismatch, p->gap);
             if (plan->scheme < 0)
                 return fail(BGSA_ERR_UNSUPPORTED, "BitPAl: scoring scheme (%d,%d,%d) has no kernel instance (see csrc/instances.h)",
                             p->match, p->mismatch, p->gap);
-            const bool ok = p->algo == BGSA_BITPAL_PACKED ? pick(kPackedTable, qlen, 77, 34, &plan->kl)
+            const bool ok = p->algo != BGSA_BITPAL_NONPACKED ? pick(kPackedTable, qlen, 77, 34, &plan->kl)
                                                           : pick(kNonPackedTable, qlen, 185, 45, &plan->kl);
             if (!ok) return fail(BGSA_ERR_UNSUPPORTED, "BitPAl: query length %d exceeds the largest kernel instance", qlen);
             return BGSA_OK;
@@ -260,6 +261,7 @@ int run_align(const Plan &plan, int sm_count, const void *d_tab, unsigned long l
         case BGSA_MYERS_SEMIGLOBAL: e = launch_myers(1, plan.kl.K, plan.kl.L, a, plan.sign); break;
         case BGSA_BITPAL_PACKED:    e = launch_bitpal_packed(plan.scheme, plan.kl.K, plan.kl.L, a); break;
         case BGSA_BITPAL_NONPACKED: e = launch_bitpal_nonpacked(plan.scheme, plan.kl.K, plan.kl.L, a); break;
+        case BGSA_BITPAL_PACKED_SEMIGLOBAL: e = launch_bitpal_semiglobal(plan.scheme, plan.kl.K, plan.kl.L, a); break;
         case BGSA_BANDED_MYERS:     e = launch_banded(a, d_tab, plan.e); break;
         default: return fail(BGSA_ERR_ARG, "unknown algorithm %d", plan.algo);
     }
@@ -309,6 +311,7 @@ int bgsa_kernel_name(const bgsa_params_t *p, int query_len, int subject_len, cha
         case BGSA_MYERS_GLOBAL: snprintf(buf, buflen, "align_kernel<MyersAlgo<K=%d,global>,L=%d>", plan.kl.K, plan.kl.L); break;
         case BGSA_MYERS_SEMIGLOBAL: snprintf(buf, buflen, "align_kernel<MyersAlgo<K=%d,semiglobal>,L=%d>", plan.kl.K, plan.kl.L); break;
         case BGSA_BITPAL_PACKED: snprintf(buf, buflen, "align_kernel<BitpalPacked<%d,%d,%d,K=%d>,L=%d>", p->match, p->mismatch, p->gap, plan.kl.K, plan.kl.L); break;
+        case BGSA_BITPAL_PACKED_SEMIGLOBAL: snprintf(buf, buflen, "align_kernel<BitpalPacked<%d,%d,%d,K=%d,semiglobal>,L=%d>", p->match, p->mismatch, p->gap, plan.kl.K, plan.kl.L); break;
         case BGSA_BITPAL_NONPACKED: snprintf(buf, buflen, "align_kernel<BitpalNonPacked<%d,%d,%d,K=%d>,L=%d>", p->match, p->mismatch, p->gap, plan.kl.K, plan.kl.L); break;
         default: snprintf(buf, buflen, "banded_kernel<%s>", 2 * plan.e + 2 <= 32 ? "u32" : "u64"); break;
     }

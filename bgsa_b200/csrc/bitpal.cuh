@@ -19,6 +19,11 @@
 // propagate unchanged through runs of d = 0 on mismatches, which one integer ADD per class
 // resolves for 32 positions at once (carry propagation = run propagation), exactly BitPAl's trick.
 //
+// Semi-global (generator -s, BitPAlGenerator.java:77-80,112-114,289-308): the whole QUERY against the best
+// substring of the SUBJECT -- S[0][t] = 0, S[p][0] = p*G, answer = max_t S[m][t].  Transposed: the top row's
+// horizontal delta is 0, i.e. e_{-1} = -G enters every column as the boundary value, and the lane that holds
+// the last query row adds up its horizontal deltas e_m + G column by column, keeping the maximum.
+//
 // "packed"     : d kept as NB = ceil(log2(A+1)) binary bit-planes (reference: two's complement of
 //                -d in NB+1 planes); y, e, T as binary planes; bit-sliced subtract/compare.
 // "non-packed" : d kept one-hot, one bit-vector per value 0..A (BitPAl's original formulation).
@@ -61,25 +66,46 @@ struct BitpalParams { int dummy; };
 // ---------------------------------------------------------------------------------------------
 // packed
 // ---------------------------------------------------------------------------------------------
-template <class S, int K_>
+enum { BITPAL_GLOBAL = 0, BITPAL_SEMIGLOBAL = 1 };
+
+template <class S, int K_, int MODE = BITPAL_GLOBAL>
 struct BitpalPacked {
     static constexpr int K = K_;
     static constexpr int A = S::A, B = S::B, NB = S::NB, NH = S::NH;
+    static constexpr bool SEMI = MODE == BITPAL_SEMIGLOBAL;
+    static constexpr int E0 = SEMI ? -S::G : 0;              // e_{-1}: horizontal delta of the top row, minus G
     using Params = BitpalParams;
-    struct State { uint32_t d[NB][K]; };
+    // cur/best/tword/tbit: semi-global only -- running S[m][t] - S[m][0], its maximum, and where this lane
+    // holds the last query row (tword < 0: it does not)
+    struct State { uint32_t d[NB][K]; int cur, best, tword, tbit; };
 
-    static BGSA_HD void init(State &s) {
+    static BGSA_HD void init(State &s, int first_bit, int qlen) {
 #pragma unroll
         for (int b = 0; b < NB; b++)
 #pragma unroll
-            for (int j = 0; j < K; j++) s.d[b][j] = 0u;      // global start: every delta = G
+            for (int j = 0; j < K; j++) s.d[b][j] = 0u;      // first column: every vertical delta = G
+        const int last = qlen - 1 - first_bit;
+        s.tword = (SEMI && last >= 0 && last < 32 * K) ? (last >> 5) : -1;
+        s.tbit = last & 31;
+        s.cur = 0; s.best = 0;
     }
 
     // carry stream (CarryIn/CarryOut, consumption order): add carry of class A; then for every lower
     // high class, top down: shift-in bit of its init vector, its add carry; then the NB shift-in
     // bits of the e planes.
     static constexpr int kCarryBits = NH + (NH > 0 ? NH - 1 : 0) + NB;
-    static constexpr uint32_t kBoundary = 0u;            // global top row: e_0 = 0, nothing propagates in
+    // what the top row hands to lane 0: e_{-1} = E0 as a carry stream (a high class enters through the shift-in
+    // bit of its init vector, every value through the e planes); global: E0 = 0, nothing propagates in
+    static __host__ __device__ constexpr bool init_in(int c) { return E0 > 0 && B + 1 + c == E0; }
+    static constexpr uint32_t boundary_word() {
+        uint32_t w = 0u;
+        if (NH > 0) w = (w << 1);                            // add carry of class A
+        for (int c = NH - 2; c >= 0; c--) { w = (w << 1) | (init_in(c) ? 1u : 0u); w = (w << 1); }
+        for (int b = 0; b < NB; b++) w = (w << 1) | ((E0 >> b) & 1);
+        return w << (32 - kCarryBits);
+    }
+    static constexpr uint32_t kBoundary = boundary_word();
+    static_assert(E0 <= A && E0 != A, "boundary value must be representable below class A");
 
     template <bool CARRY>
     static BGSA_HD uint32_t column(State &s, const uint32_t *row, uint32_t cin) {
@@ -130,7 +156,7 @@ struct BitpalPacked {
                     for (int dl = 1; c + dl <= NH - 1; dl++) v |= D[dl][j] & Y[c + dl][j];
                     init[j] = v;                              // e_p == k at a position with d != 0
                 }
-                const uint32_t sin = CARRY ? in.top() : 0u;
+                const uint32_t sin = CARRY ? in.top() : (init_in(c) ? 0x80000000u : 0u);
 #pragma unroll
                 for (int j = 0; j < K; j++) sh[j] = shl1_carry(j ? init[j - 1] : sin, init[j]);
                 if (CARRY) { out.push_top(init[K - 1]); in.to_cf(); }
@@ -143,7 +169,7 @@ struct BitpalPacked {
         // ---- binary planes of y, then e = max(0, y - d), T = max(y, d), d' = T - (e << 1)
         uint32_t e_prev[NB];
 #pragma unroll
-        for (int b = 0; b < NB; b++) e_prev[b] = CARRY ? in.top() : 0u;   // e_0 = 0: global top row
+        for (int b = 0; b < NB; b++) e_prev[b] = CARRY ? in.top() : (((E0 >> b) & 1) ? 0x80000000u : 0u);   // top row
 #pragma unroll
         for (int j = 0; j < K; j++) {
             uint32_t hi = 0u;
@@ -172,6 +198,13 @@ struct BitpalPacked {
                 e[b] = diff[b] & ~lt;
                 T[b] = (lt & s.d[b][j]) | (~lt & y[b]);
             }
+            if (SEMI && j == s.tword) {                      // horizontal delta of the last query row
+                int v = 0;
+#pragma unroll
+                for (int b = 0; b < NB; b++) v += (int)((e[b] >> s.tbit) & 1u) << b;
+                s.cur += v + S::G;
+                s.best = s.cur > s.best ? s.cur : s.best;
+            }
             // shift e one position up (e_{p-1} aligned with p), then d' = T - es
             uint32_t br2 = 0u;
 #pragma unroll
@@ -192,16 +225,21 @@ struct BitpalPacked {
 
     static BGSA_HD Partial partial(const State &s, int first_bit, int qlen) {
         Partial r; r.sum = 0; r.minpre = 0;
+        if (SEMI) {                                          // only the lane with the last query row has the answer
+            r.minpre = s.tword >= 0 ? -s.best : 0x3fffffff;
+        } else {
 #pragma unroll
-        for (int j = 0; j < K; j++) {
-            const int rem = qlen - first_bit - 32 * j;
-            const uint32_t mask = rem >= 32 ? 0xffffffffu : (rem <= 0 ? 0u : ((1u << rem) - 1u));
+            for (int j = 0; j < K; j++) {
+                const int rem = qlen - first_bit - 32 * j;
+                const uint32_t mask = rem >= 32 ? 0xffffffffu : (rem <= 0 ? 0u : ((1u << rem) - 1u));
 #pragma unroll
-            for (int b = 0; b < NB; b++) r.sum += popc32(s.d[b][j] & mask) << b;
+                for (int b = 0; b < NB; b++) r.sum += popc32(s.d[b][j] & mask) << b;
+            }
         }
         return r;
     }
-    static BGSA_HD int final_score(int sum, int, int qlen, int slen, Params) {
+    static BGSA_HD int final_score(int sum, int minpre, int qlen, int slen, Params) {
+        if (SEMI) return (S::G * qlen - minpre) * S::F;      // S[m][0] + max_t (S[m][t] - S[m][0])
         return (S::G * (qlen + slen) + sum) * S::F;
     }
 };
@@ -217,7 +255,7 @@ struct BitpalNonPacked {
     using Params = BitpalParams;
     struct State { uint32_t d[A][K]; };        // d[v-1][j] = [d == v]
 
-    static BGSA_HD void init(State &s) {
+    static BGSA_HD void init(State &s, int, int) {
 #pragma unroll
         for (int v = 0; v < A; v++)
 #pragma unroll

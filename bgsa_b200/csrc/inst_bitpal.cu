@@ -1,5 +1,6 @@
-// inst_bitpal.cu -- BitPAl kernel instances for ONE scoring scheme and ONE state encoding
-// (compiled once per (scheme, packed?) so that the heavy instances build in parallel).
+// inst_bitpal.cu -- BitPAl kernel instances for ONE scoring scheme and ONE variant (BGSA_PACKED: 0 non-packed,
+// 1 packed global, 2 packed semi-global), compiled once per (scheme, variant) so that the heavy instances build
+// in parallel.
 #include "instances.h"
 #include "launch.cuh"
 #include "bitpal.cuh"
@@ -15,7 +16,15 @@ namespace bgsa {
 
 using TheScheme = Scheme<BGSA_M, BGSA_I, BGSA_G>;
 
-#if BGSA_PACKED
+#if BGSA_PACKED == 2
+cudaError_t BGSA_CAT(launch_bitpal_semiglobal_s, BGSA_SCHEME_ID)(int K, int L, const LaunchArgs &a) {
+#define X(k, l) \
+    if (K == k && L == l) return launch_align<BitpalPacked<TheScheme, k, BITPAL_SEMIGLOBAL>, l, 2>(a, BitpalParams{0});
+    BGSA_BITPAL_PACKED_INSTANCES(X)
+#undef X
+    return cudaErrorInvalidValue;
+}
+#elif BGSA_PACKED
 cudaError_t BGSA_CAT(launch_bitpal_packed_s, BGSA_SCHEME_ID)(int K, int L, const LaunchArgs &a) {
 #define X(k, l) \
     if (K == k && L == l) return launch_align<BitpalPacked<TheScheme, k>, l, 2>(a, BitpalParams{0});

@@ -14,6 +14,7 @@ cudaError_t launch_myers_global(int K, int L, const LaunchArgs &a, int sign);
 cudaError_t launch_myers_semiglobal(int K, int L, const LaunchArgs &a, int sign);
 #define X(id, m, i, g)                                                              \
     cudaError_t launch_bitpal_packed_s##id(int K, int L, const LaunchArgs &a);     \
+    cudaError_t launch_bitpal_semiglobal_s##id(int K, int L, const LaunchArgs &a); \
     cudaError_t launch_bitpal_nonpacked_s##id(int K, int L, const LaunchArgs &a);
 BGSA_SCHEMES(X)
 #undef X
@@ -23,6 +24,12 @@ cudaError_t launch_myers(int mode, int K, int L, const LaunchArgs &a, int sign) 
 }
 cudaError_t launch_bitpal_packed(int scheme, int K, int L, const LaunchArgs &a) {
 #define X(id, m, i, g) if (scheme == id) return launch_bitpal_packed_s##id(K, L, a);
+    BGSA_SCHEMES(X)
+#undef X
+    return cudaErrorInvalidValue;
+}
+cudaError_t launch_bitpal_semiglobal(int scheme, int K, int L, const LaunchArgs &a) {
+#define X(id, m, i, g) if (scheme == id) return launch_bitpal_semiglobal_s##id(K, L, a);
     BGSA_SCHEMES(X)
 #undef X
     return cudaErrorInvalidValue;

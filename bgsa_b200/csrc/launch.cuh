@@ -54,6 +54,7 @@ cudaError_t launch_align(const LaunchArgs &a, typename Algo::Params prm) {
 // instance-file entry points (return cudaErrorInvalidValue when (K, L) has no instance)
 cudaError_t launch_myers(int mode, int K, int L, const LaunchArgs &a, int sign);
 cudaError_t launch_bitpal_packed(int scheme, int K, int L, const LaunchArgs &a);
+cudaError_t launch_bitpal_semiglobal(int scheme, int K, int L, const LaunchArgs &a);
 cudaError_t launch_bitpal_nonpacked(int scheme, int K, int L, const LaunchArgs &a);
 cudaError_t launch_banded(const LaunchArgs &a, const void *d_rows_table, int e);
 cudaError_t launch_pack(int layout, const void *d_rows, int slen, long long count, void *d_packed, int sm_count,

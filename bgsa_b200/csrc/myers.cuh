@@ -33,7 +33,7 @@ struct MyersAlgo {
     // carry stream (CarryIn/CarryOut, consumption order): add carry, Ph shift-in, Mh shift-in
     static constexpr uint32_t kBoundary = 0x40000000u;   // top row: no carry, D[0][i] - D[0][i-1] = +1 (Ph), Mh 0
 
-    static BGSA_HD void init(State &s) {
+    static BGSA_HD void init(State &s, int, int) {
 #pragma unroll
         for (int j = 0; j < K; j++) { s.pv[j] = (MODE == MYERS_GLOBAL) ? 0xffffffffu : 0u; s.mv[j] = 0u; }
     }

@@ -12,7 +12,7 @@
  *
  * Reference options keep their meaning: -q -d -f, -N (host threads: accepted, unused), -k (banded
  * threshold).  Additive options (the reference bakes these into the generated align_core.c):
- *   -a myers | semiglobal | banded | bitpal | bitpal-nonpacked     algorithm   (default myers)
+ *   -a myers | semiglobal | banded | bitpal | bitpal-nonpacked | bitpal-semiglobal     algorithm   (default myers)
  *   -M <match> -I <mismatch> -G <gap>                              BitPAl scores (default 2 -3 -5)
  *   -m 0|1                                                         Myers sign: 0 = -distance (default), 1 = +distance
  *   -g <n>                                                         number of GPUs (default 1): contiguous subject
@@ -59,7 +59,7 @@ static void print_help(void) {
     printf("  -d <arg>\n\t Database file (one sequence per line, equal lengths).\n\n");
     printf("  -f <arg>\n\t Alignment result file. \n\n");
     printf("  -k <arg>\n\t Filter threshold (banded). \n\n");
-    printf("  -a <arg>\n\t Algorithm: myers | semiglobal | banded | bitpal | bitpal-nonpacked. \n\n");
+    printf("  -a <arg>\n\t Algorithm: myers | semiglobal | banded | bitpal | bitpal-nonpacked | bitpal-semiglobal. \n\n");
     printf("  -M/-I/-G <arg>\n\t BitPAl match / mismatch / gap scores (default 2 -3 -5). \n\n");
     printf("  -g <arg>\n\t Number of GPUs. \n\n");
     exit(1);
@@ -90,6 +90,7 @@ int main(int argc, char **argv) {
                 else if (!strcmp(optarg, "banded")) algo = BGSA_BANDED_MYERS;
                 else if (!strcmp(optarg, "bitpal")) algo = BGSA_BITPAL_PACKED;
                 else if (!strcmp(optarg, "bitpal-nonpacked")) algo = BGSA_BITPAL_NONPACKED;
+                else if (!strcmp(optarg, "bitpal-semiglobal")) algo = BGSA_BITPAL_PACKED_SEMIGLOBAL;
                 else print_help();
                 break;
             case 'M': M = atoi(optarg); break;
@@ -105,7 +106,7 @@ int main(int argc, char **argv) {
     if (!file_database) { printf("Database file can't be empty. \n"); exit(1); }   /* main.c:96-99 */
     if (ngpu < 1 || ngpu > MAX_GPUS) die("Error - bad GPU count: %s", "-g");
     bgsa_params_default(&prm, algo);
-    if (algo == BGSA_BITPAL_PACKED || algo == BGSA_BITPAL_NONPACKED) { prm.match = M; prm.mismatch = I; prm.gap = G; }
+    if (algo == BGSA_BITPAL_PACKED || algo == BGSA_BITPAL_NONPACKED || algo == BGSA_BITPAL_PACKED_SEMIGLOBAL) { prm.match = M; prm.mismatch = I; prm.gap = G; }
     prm.threshold = threshold;
     prm.myers_sign = sign;
     const int esize = bgsa_result_size(algo);

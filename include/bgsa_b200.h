@@ -44,7 +44,9 @@ typedef enum bgsa_algo_t {
     BGSA_MYERS_SEMIGLOBAL = 1, /* generator -m -s, MyersGenerator.java:56-223                     */
     BGSA_BANDED_MYERS = 2,     /* generator -b, banded/BGSA_CPU/align_core.c, result int8         */
     BGSA_BITPAL_PACKED = 3,    /* generator -M -I -G, original/BGSA_AVX512/align_core.c           */
-    BGSA_BITPAL_NONPACKED = 4  /* generator -t non-packed, BitPAlGenerator.java:1392-1701         */
+    BGSA_BITPAL_NONPACKED = 4, /* generator -t non-packed, BitPAlGenerator.java:1392-1701         */
+    BGSA_BITPAL_PACKED_SEMIGLOBAL = 5 /* generator -s with -M/-I/-G: whole query inside the subject,
+                                  BitPAlGenerator.java:77-80,112-114,289-308                      */
 } bgsa_algo_t;
 
 /* What the reference bakes into the generated align_core.c (align_core.c:13-17) plus -k. */

@@ -322,7 +322,7 @@ static int16_t bitpal_finish(const bitpal_cfg *c, int qlen, int slen, int64_t su
  *   bit-sliced add + e_{p-1}, keep only negatives -> new -d (:391-428).
  * with w = A on a match and B on a mismatch.
  * ---------------------------------------------------------------------------------------- */
-int16_t oracle_bitpal_packed(const char *q, int qlen, const char *s, int slen, int M, int I, int G) {
+static int16_t bitpal_packed_core(const char *q, int qlen, const char *s, int slen, int M, int I, int G, int semi) {
     bitpal_cfg cfg;
     if (bitpal_setup(&cfg, M, I, G)) return 0;
     const int A = cfg.A, B = cfg.B, nb = cfg.nb;
@@ -344,6 +344,13 @@ int16_t oracle_bitpal_packed(const char *q, int qlen, const char *s, int slen, i
 #undef TAKE
 #define V(base, k) ((base) + (size_t)(k) * nw)
     uint64_t valid_last = (slen % W63) ? ((1ULL << (slen % W63)) - 1) : MASK63;
+    if (semi) {
+        /* writeBitInitStr (BitPAlGenerator.java:289-291,2201-2218): every delta along the subject starts at 0,
+         * i.e. d = -G, planes = two's complement of G */
+        const unsigned pat = ((1u << nb) - (unsigned)(-cfg.G)) & full;
+        for (int b = 0; b < nb; b++)
+            for (int j = 0; j < nw; j++) V(S, b)[j] = ((pat >> b) & 1) ? MASK63 : 0;
+    }
 
     for (int col = 0; col < qlen; col++) {
         const uint64_t *eq = &peq[(int)q[col] * nw];
@@ -430,6 +437,24 @@ int16_t oracle_bitpal_packed(const char *q, int qlen, const char *s, int slen, i
         }
         (void)carry; (void)tmp;
     }
+    if (semi) {
+        /* genPackedScore with isSemiGlobal (BitPAlGenerator.java:67-148): score = G*ref_len, then one subject
+         * position at a time score += delta, max_score = max(max_score, score); max_score * factor -> int16 */
+        int64_t score = (int64_t)cfg.G * qlen, best = score;
+        for (int i = 0; i < slen; i++) {
+            const int j = i / W63, bit = i % W63;
+            int64_t negd = 0;
+            for (int b = 0; b < nb; b++) {
+                const int64_t v = (int64_t)((V(S, b)[j] >> bit) & 1) << b;
+                if (b == nb - 1) negd -= v; else negd += v;          /* two's complement value of the planes = -d */
+            }
+            score += -negd + cfg.G;
+            if (score > best) best = score;
+        }
+        free(mem); free(peq);
+        best *= cfg.factor;
+        return (int16_t)(int32_t)(uint32_t)(uint64_t)best;
+    }
     /* score (:432-471): planes hold -d as nb-bit two's complement */
     int64_t sum_d = 0;
     for (int j = 0; j < nw; j++) {
@@ -442,6 +467,16 @@ int16_t oracle_bitpal_packed(const char *q, int qlen, const char *s, int slen, i
     free(mem); free(peq);
     return bitpal_finish(&cfg, qlen, slen, sum_d);
 #undef V
+}
+
+int16_t oracle_bitpal_packed(const char *q, int qlen, const char *s, int slen, int M, int I, int G) {
+    return bitpal_packed_core(q, qlen, s, slen, M, I, G, 0);
+}
+/* BitPAl packed, semi-global (generator -s; BitPAlGenerator.java:77-80,112-114,289-308): the whole QUERY aligned
+ * to the best substring of the SUBJECT.  No reference artefact exists for it (the
+ * generator needs a JRE): "parity unpinned", checked against plain DP only. */
+int16_t oracle_bitpal_packed_semiglobal(const char *q, int qlen, const char *s, int slen, int M, int I, int G) {
+    return bitpal_packed_core(q, qlen, s, slen, M, I, G, 1);
 }
 
 /* ------------------------------------------------------------------------------------------
@@ -572,6 +607,25 @@ int oracle_dp_nw(const char *q, int qlen, const char *s, int slen, int M, int I,
     int r = row[slen]; free(row); return r;
 }
 
+/* whole query inside the subject: S[0][j] = 0, S[i][0] = i*G, answer = max_j S[qlen][j] */
+int oracle_dp_nw_semiglobal(const char *q, int qlen, const char *s, int slen, int M, int I, int G) {
+    int *row = (int *)malloc(sizeof(int) * (slen + 1));
+    for (int j = 0; j <= slen; j++) row[j] = 0;
+    for (int i = 1; i <= qlen; i++) {
+        int diag = row[0]; row[0] = i * G;
+        for (int j = 1; j <= slen; j++) {
+            int up = row[j];
+            int best = diag + (((int)q[i - 1] == oracle_map_char((unsigned char)s[j - 1])) ? M : I);
+            if (up + G > best) best = up + G;
+            if (row[j - 1] + G > best) best = row[j - 1] + G;
+            diag = up; row[j] = best;
+        }
+    }
+    int r = row[0];
+    for (int j = 1; j <= slen; j++) if (row[j] > r) r = row[j];
+    free(row); return r;
+}
+
 int oracle_dp_semiglobal(const char *q, int qlen, const char *s, int slen) {
     /* rows = subject (must be consumed), columns = query (free start and end) */
     int *col = (int *)malloc(sizeof(int) * (slen + 1));
@@ -599,7 +653,7 @@ int oracle_align_batch(int algo, int M, int I, int G, int e,
                        const char *subjects, int64_t n_subjects, int slen,
                        void *out, int threads) {
     if (!queries || !subjects || !out || qlen <= 0 || slen <= 0 || n_queries < 0 || n_subjects < 0) return -1;
-    if (algo < ORACLE_MYERS_GLOBAL || algo > ORACLE_BITPAL_NONPACKED) return -1;
+    if (algo < ORACLE_MYERS_GLOBAL || algo > ORACLE_BITPAL_PACKED_SEMIGLOBAL) return -1;
     if (algo >= ORACLE_BITPAL_PACKED) { bitpal_cfg c; if (bitpal_setup(&c, M, I, G)) return -1; }
 #ifdef _OPENMP
     if (threads <= 0) threads = omp_get_max_threads();
@@ -618,6 +672,8 @@ int oracle_align_batch(int algo, int M, int I, int G, int e,
             case ORACLE_BANDED_MYERS:     ((int8_t *)out)[t]  = oracle_banded_myers(q, qlen, s, slen, e); break;
             case ORACLE_BITPAL_PACKED:    ((int16_t *)out)[t] = oracle_bitpal_packed(q, qlen, s, slen, M, I, G); break;
             case ORACLE_BITPAL_NONPACKED: ((int16_t *)out)[t] = oracle_bitpal_nonpacked(q, qlen, s, slen, M, I, G); break;
+            case ORACLE_BITPAL_PACKED_SEMIGLOBAL:
+                ((int16_t *)out)[t] = oracle_bitpal_packed_semiglobal(q, qlen, s, slen, M, I, G); break;
         }
     }
     return 0;

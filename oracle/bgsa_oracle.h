@@ -27,7 +27,8 @@ enum {
     ORACLE_MYERS_SEMIGLOBAL = 1, /* generator/.../MyersGenerator.java:56-223                  */
     ORACLE_BANDED_MYERS = 2,     /* banded/BGSA_CPU/align_core.c:69-252                       */
     ORACLE_BITPAL_PACKED = 3,    /* original/BGSA_AVX512/align_core.c:19-485                  */
-    ORACLE_BITPAL_NONPACKED = 4  /* generator/.../BitPAlGenerator.java:939-1061,1392-1701     */
+    ORACLE_BITPAL_NONPACKED = 4, /* generator/.../BitPAlGenerator.java:939-1061,1392-1701     */
+    ORACLE_BITPAL_PACKED_SEMIGLOBAL = 5 /* generator -s: BitPAlGenerator.java:77-80,112-114,289-308 */
 };
 
 /* global.c:9-15 -- A,C,G,T,N -> 0..4, every other byte -> 0 */
@@ -43,10 +44,13 @@ int8_t oracle_banded_myers(const char *q, int qlen, const char *s, int slen, int
 int8_t oracle_banded_myers_w(const char *q, int qlen, const char *s, int slen, int e, int wordbits);
 int16_t oracle_bitpal_packed(const char *q, int qlen, const char *s, int slen, int M, int I, int G);
 int16_t oracle_bitpal_nonpacked(const char *q, int qlen, const char *s, int slen, int M, int I, int G);
+int16_t oracle_bitpal_packed_semiglobal(const char *q, int qlen, const char *s, int slen, int M, int I, int G);
 
 /* Plain dynamic programming (independent mathematical cross-check; no narrowing). */
 int oracle_dp_edit(const char *q, int qlen, const char *s, int slen);
 int oracle_dp_nw(const char *q, int qlen, const char *s, int slen, int M, int I, int G);
+/* max over substrings of s of the NW score of the WHOLE of q against it (Appendix A9, BitPAl orientation) */
+int oracle_dp_nw_semiglobal(const char *q, int qlen, const char *s, int slen, int M, int I, int G);
 /* min over substrings of q of edit distance to the WHOLE of s (Appendix A9, Myers orientation) */
 int oracle_dp_semiglobal(const char *q, int qlen, const char *s, int slen);
 

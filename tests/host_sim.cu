@@ -34,7 +34,7 @@ static int run_pair(const char *qcodes, int qlen, const char *subject, int slen,
     while (reinterpret_cast<uintptr_t>(peq) & 15) peq++;      // LDS.128-style loads need 16-B alignment
     build_query_peq(qcodes, qlen, K, L, peq);
     std::vector<typename Algo::State> st(L);
-    for (auto &s : st) Algo::init(s);
+    for (int r = 0; r < L; r++) Algo::init(st[r], r * K * 32, qlen);
     std::vector<uint32_t> packet(L, 0u), next(L, 0u);
     for (int t = 0; t < slen + L - 1; t++) {
         for (int r = 0; r < L; r++) {
@@ -72,7 +72,7 @@ static void run_batch(const char *queries, int nq, int qlen, const char *subject
 
 extern "C" {
 
-// algo: 0 Myers global, 1 Myers semi-global, 3 BitPAl packed, 4 BitPAl non-packed (bgsa_algo_t).
+// algo: 0 Myers global, 1 Myers semi-global, 3 BitPAl packed, 4 BitPAl non-packed, 5 BitPAl packed semi-global (bgsa_algo_t).
 // (K, L) must be one of the instances of csrc/instances.h; scheme = index into BGSA_SCHEMES.
 // Returns 0, or -1 when (algo, scheme, K, L) is not an instance.
 int host_sim_align(int algo, int scheme, int K, int L, int sign, const char *queries, int nq, int qlen,
@@ -94,16 +94,20 @@ int host_sim_align(int algo, int scheme, int K, int L, int sign, const char *que
         using Sch = Scheme<m, i, g>;                                                                         \
         if (algo == 3) {                                                                                     \
             BGSA_BITPAL_PACKED_INSTANCES(XP)                                                                 \
+        } else if (algo == 5) {                                                                              \
+            BGSA_BITPAL_PACKED_INSTANCES(XS)                                                                 \
         } else if (algo == 4) {                                                                              \
             BGSA_BITPAL_NONPACKED_INSTANCES(XN)                                                              \
         }                                                                                                    \
         return -1;                                                                                           \
     }
 #define XP(k, l) if (K == k && L == l) { run_batch<BitpalPacked<Sch, k>, l>(queries, nq, qlen, subjects, ns, slen, BitpalParams{0}, out); return 0; }
+#define XS(k, l) if (K == k && L == l) { run_batch<BitpalPacked<Sch, k, BITPAL_SEMIGLOBAL>, l>(queries, nq, qlen, subjects, ns, slen, BitpalParams{0}, out); return 0; }
 #define XN(k, l) if (K == k && L == l) { run_batch<BitpalNonPacked<Sch, k>, l>(queries, nq, qlen, subjects, ns, slen, BitpalParams{0}, out); return 0; }
     BGSA_SCHEMES(S)
 #undef S
 #undef XP
+#undef XS
 #undef XN
     return -1;
 }

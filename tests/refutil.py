@@ -16,7 +16,7 @@ ROOT = Path(__file__).resolve().parent.parent
 ORACLE_DIR = ROOT / "oracle"
 REF_DIR = ORACLE_DIR / "_ref"
 
-ALGO_MYERS_GLOBAL, ALGO_MYERS_SEMIGLOBAL, ALGO_BANDED, ALGO_BITPAL_PACKED, ALGO_BITPAL_NONPACKED = range(5)
+ALGO_MYERS_GLOBAL, ALGO_MYERS_SEMIGLOBAL, ALGO_BANDED, ALGO_BITPAL_PACKED, ALGO_BITPAL_NONPACKED, ALGO_BITPAL_SEMI = range(6)
 
 _ACGT = np.frombuffer(b"ACGT", dtype=np.uint8)
 _MAP = np.zeros(256, dtype=np.uint8)
@@ -120,8 +120,9 @@ def oracle():
         for name in ("oracle_dp_edit", "oracle_dp_semiglobal"):
             f = getattr(lib, name); f.restype = C.c_int
             f.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
-        lib.oracle_dp_nw.restype = C.c_int
-        lib.oracle_dp_nw.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
+        for name in ("oracle_dp_nw", "oracle_dp_nw_semiglobal"):
+            f = getattr(lib, name); f.restype = C.c_int
+            f.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
         _oracle = lib
     return _oracle
 
@@ -155,6 +156,8 @@ def dp_scores(kind: str, queries: np.ndarray, subjects: np.ndarray, M=2, I=-3, G
                 out[i, j] = lib.oracle_dp_edit(qa, qlen, sa, slen)
             elif kind == "semi":
                 out[i, j] = lib.oracle_dp_semiglobal(qa, qlen, sa, slen)
+            elif kind == "nw_semi":
+                out[i, j] = lib.oracle_dp_nw_semiglobal(qa, qlen, sa, slen, M, I, G)
             else:
                 out[i, j] = lib.oracle_dp_nw(qa, qlen, sa, slen, M, I, G)
     return out

@@ -102,6 +102,28 @@ def test_all_geometries_vs_oracle(B, ql, sl, ns):
         assert (gpu(B, B.BITPAL_NONPACKED, q, s, **kw) == expect(3, q, s, **kw)).all()
 
 
+@pytest.mark.parametrize("ql,sl,ns", [(150, 150, 500), (100, 400, 333), (37, 150, 65), (150, 37, 65), (500, 800, 100), (1, 9, 33),
+                                      (320, 321, 70), (1500, 2500, 40), (5000, 5300, 33), (5000, 700, 33), (64, 64, 64)])
+def test_bitpal_semiglobal_vs_oracle_and_dp(B, ql, sl, ns):
+    """BitPAl semi-global (whole query inside the subject): no reference build exists
+    (the generator needs a JRE) -- parity is against the restated emission (oracle) and, on a sample, plain DP."""
+    rng = np.random.default_rng(ql * 17 + sl)
+    q = R.random_rows(rng, 2, ql, with_n=0.01)
+    s = R.random_rows(rng, ns, sl, with_n=0.01)
+    if sl >= ql:
+        for i in range(ns // 3):
+            off = int(rng.integers(0, sl - ql + 1))
+            s[i, off:off + ql] = q[i % 2, :ql]
+    for M, I, G in ((2, -3, -5), (1, -1, -1), (1, -3, -2)):
+        p = B.Params.default(B.BITPAL_PACKED_SEMIGLOBAL, match=M, mismatch=I, gap=G)
+        got = B.align_batch(p, q, s)
+        assert (got == R.oracle_batch(R.ALGO_BITPAL_SEMI, q, s, M=M, I=I, G=G)).all(), (M, I, G, ql, sl)
+        if ql * sl <= 250_000:
+            assert (got[:, :8] == R.dp_scores("nw_semi", q, s[:8], M=M, I=I, G=G)).all()
+        if sl >= ql:
+            assert (got[0, 0] == M * ql) or ns < 3          # a planted exact copy scores M per base
+
+
 def test_myers_long_queries(B):
     rng = np.random.default_rng(3)
     for ql, sl in ((16384, 300), (20000, 150), (32768, 100)):

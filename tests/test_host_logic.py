@@ -131,6 +131,27 @@ def test_bitpal_columns_on_host(sim, scheme, mig, packed):
             assert (got == R.oracle_batch(R.ALGO_BITPAL_PACKED, q, s, M=M, I=I, G=G)).all(), (K, L, ql, sl)
 
 
+@pytest.mark.parametrize("scheme,mig", [(0, (2, -3, -5)), (1, (1, -1, -1)), (2, (1, -3, -2))])
+def test_bitpal_semiglobal_columns_on_host(sim, scheme, mig):
+    """Semi-global BitPAl (whole query inside the subject): every (K, L) instance on the host against the
+    restated generator emission AND plain DP.  Scheme 2 has -G in a high class (boundary enters a carry chain)."""
+    rng = np.random.default_rng(300 + scheme)
+    M, I, G = mig
+    for K, L in _instances("BGSA_BITPAL_PACKED_INSTANCES"):
+        cap = min(32 * K * L, 900)
+        for ql in {cap, max(1, cap - 33), max(1, cap // 2 + 1)}:
+            sl = int(rng.integers(max(1, ql // 2), 2 * ql + 20))
+            q = R.random_rows(rng, 1, ql, with_n=0.02)
+            s = R.random_rows(rng, 3, sl, with_n=0.02)
+            if sl > ql + 4:
+                s[0, 3:3 + ql] = q[0, :ql]                      # the query planted inside a subject
+            s[1, : min(ql, sl)] = q[0, : min(ql, sl)]
+            rc, got = run_sim(sim, 5, scheme, K, L, q, s)
+            assert rc == 0
+            assert (got == R.oracle_batch(R.ALGO_BITPAL_SEMI, q, s, M=M, I=I, G=G)).all(), (K, L, ql, sl)
+            assert (got == R.dp_scores("nw_semi", q, s, M=M, I=I, G=G).astype(np.int16)).all(), (K, L, ql, sl)
+
+
 def test_shard_counts():
     from bgsa_b200.sharding import shard_counts, shard_range
     assert shard_counts(1_000_000, 8) == [124992] * 7 + [125056]

@@ -61,4 +61,6 @@ run("C4", B.MYERS_SEMIGLOBAL, 1000, 1000, 300_000)
 run("C5", B.BITPAL_PACKED, 5000, 5000, 8192, reps=4)
 run("C2np", B.BITPAL_NONPACKED, 150, 150, 300_000)
 run("bp111", B.BITPAL_PACKED, 150, 150, 1_000_000, match=1, mismatch=-1, gap=-1)
+run("C2semi", B.BITPAL_PACKED_SEMIGLOBAL, 150, 150, 1_000_000)
+run("C5semi", B.BITPAL_PACKED_SEMIGLOBAL, 5000, 5000, 8192, reps=4)
 run("myers5k", B.MYERS_GLOBAL, 5000, 5000, 16384, reps=4)
