@@ -282,10 +282,13 @@ def main():
     except (OSError, ValueError):
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    # roofline.traffic: DRAM bytes of the align kernel per launch, from the committed ncu --set full capture of the
+    # same kernel (profiles/ncu_summary.json, written by tools/ncu_summarize.py), scaled to this launch's subjects
     traffic = None
     try:
-        prof = json.loads((ROOT / "profiles" / "ncu_summary.json").read_text())
-        traffic = prof.get(args.workload, {}).get("dram_bytes_per_launch")
+        prof = json.loads((ROOT / "profiles" / "ncu_summary.json").read_text()).get(args.workload, {})
+        if "dram_bytes_per_subject" in prof:
+            traffic = prof["dram_bytes_per_subject"] * ns
     except (OSError, ValueError):
         pass
     line = {
