@@ -132,6 +132,18 @@ def reference_run(wl: dict, query, subjects, min_seconds: float, max_runs: int):
                 gcups_path=cells / (th + tc) / 1e9, gcups_cal=cells / tc / 1e9, scores=scores)
 
 
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout: anything a library prints there (NCCL's version banner under
+    NCCL_DEBUG=VERSION, for one) goes to stderr instead; the returned writer emits on the real stdout."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        os.write(real, (json.dumps(obj) + "\n").encode())
+    return emit
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -153,6 +165,7 @@ def main():
         # convenience: re-launch ourselves one rank per GPU
         os.execvp(sys.executable, [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                                    "--master-addr", "127.0.0.1", "--master-port", "29517", __file__] + sys.argv[1:])
+    emit = _claim_stdout()
 
     cfg = synth.CONFIGS[wl["cfg"]]
     qlen, slen = cfg["qlen"], cfg["slen"]
@@ -167,17 +180,17 @@ def main():
         query, subjects = synth.make(wl["cfg"], count)
         res = reference_run(wl, query, subjects, min_seconds=20.0, max_runs=max(args.steps + args.warmup, 3))
         if res is None:
-            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built for this host CPU"}))
+            emit({"impl": "reference", "unavailable": "oracle/_ref not built for this host CPU"})
             return
         v = res["gcups_path"]
-        print(json.dumps({
+        emit({
             "impl": "reference", "metric": "GCUPS", "value": v, "unit": "GCUPS", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * (res["t_handle"] + res["t_cal"]), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic", "config": config,
             "cpu_baseline": {"value": v, "unit": "GCUPS", "cores": res["cores"], "kind": res["kind"], "variant": res["variant"],
                              "sample": f"full workload ({subjects.shape[0]} subjects), best of {res['runs']} runs, Peq build + kernel",
                              "cal_only_gcups": res["gcups_cal"]},
-            "e2e": {"value": v, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+            "e2e": {"value": v, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
         return
 
     # ---------------------------------------------------------------- our arm
@@ -325,7 +338,7 @@ def main():
             mism = int((out_pinned[:, :nref] != res["scores"]).sum())
             line["parity"] = {"against": res["variant"], "subjects_compared": int(nref), "mismatches": mism,
                               "crc32_all_scores": "%08x" % zlib.crc32(out_pinned.tobytes())}
-    print(json.dumps(line))
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
 
