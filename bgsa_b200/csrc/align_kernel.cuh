@@ -10,6 +10,7 @@
 //         (a CarryIn stream, top-aligned, bits 0..2 ignored) and the carry-outs are returned as
 //         a CarryOut stream with bits 0..2 clear.
 //     static constexpr uint32_t kBoundary;            // carry-in bits at the top row (lane 0)
+//     static constexpr int kOpsPerWord;               // rough ALU instructions per word-column (unrolling policy)
 //     static Partial partial(const State&, int first_bit, int qlen);   // per-lane score pieces
 //     static int final_score(sum, min_prefix, qlen, slen, Params);     // 32-bit score
 //
@@ -43,8 +44,14 @@ struct Partial { int sum; int minpre; };   // segment sum of deltas, minimum pre
 __host__ __device__ constexpr int peq_kp(int k) { return (k + 3) / 4 * 4; }
 __host__ __device__ constexpr int peq_row_stride(int k, int lanes) { return peq_stride(peq_kp(k) * lanes); }
 
+// BGSA_MIN_BLOCKS: second __launch_bounds__ argument.  Without it ptxas caps the big instances at 128 registers
+// and spills (K >= 8: -25 % on C5); with 1 it takes what the instance needs (measured: profiles/r01_minblocks_ab_mb{0,1}.log).
+#ifndef BGSA_MIN_BLOCKS
+#define BGSA_MIN_BLOCKS 1
+#endif
+
 template <class Algo, int L, int CH, int THREADS, int UNROLL>
-__global__ void __launch_bounds__(THREADS)
+__global__ void __launch_bounds__(THREADS, BGSA_MIN_BLOCKS)
 align_kernel(PackedSubjects ps, const uint32_t *__restrict__ g_peq, int qlen, int16_t *__restrict__ results,
              long long result_stride, typename Algo::Params prm, unsigned long long *__restrict__ counters) {
     constexpr int K = Algo::K;
@@ -52,6 +59,7 @@ align_kernel(PackedSubjects ps, const uint32_t *__restrict__ g_peq, int qlen, in
     constexpr int STRIDE = peq_row_stride(K, L);
     constexpr int WARPS = THREADS / 32;
     constexpr int GROUPS = 32 / L;                 // subjects in flight per warp
+    constexpr int WUNROLL = (K * Algo::kOpsPerWord <= 100) ? 4 : 1;
     __shared__ __align__(16) uint32_t s_peq[kPeqRows * STRIDE];
     __shared__ __align__(128) uint4 s_stage[WARPS * 2 * CH * 32];
     __shared__ __align__(8) uint64_t s_bar[WARPS * 2];
@@ -118,6 +126,7 @@ align_kernel(PackedSubjects ps, const uint32_t *__restrict__ g_peq, int qlen, in
                     st.issue(sb ^ 1, ps.codes + (nxt / L) * ku * 32, min(CH, ku), lane);
                 st.wait(sb);
                 const int units = min(CH, ku - sg * CH);
+#pragma unroll 1
                 for (int u = 0; u < units; u++) {
                     const uint4 v = st.load(sb, u, sidx);
                     const int base0 = (sg * CH + u) * kBasesPerUnit;
@@ -127,7 +136,9 @@ align_kernel(PackedSubjects ps, const uint32_t *__restrict__ g_peq, int qlen, in
                         n0 = ps.nmask[(tile * ps.kn + kk) * 32 + sidx];
                         if (kk + 1 < ps.kn) n1 = ps.nmask[(tile * ps.kn + kk + 1) * 32 + sidx];
                     }
-#pragma unroll
+                    // The body holds UNROLL + 2 copies of the column: unrolled 4x more only where a column is small
+                    // (big instances would overflow the instruction cache -- measured -25 % on BitPAl K=10).
+#pragma unroll (WUNROLL)
                     for (int w = 0; w < 4; w++) {
                         const int nb = min(16, slen - base0 - 16 * w);
                         uint32_t word = (w == 0) ? v.x : (w == 1) ? v.y : (w == 2) ? v.z : v.w;

@@ -202,7 +202,8 @@ int get_ctx(int device, DeviceCtx **out) {
 // Build (or reuse) the query-side tables on the device.  Returns the device pointer in *d_tab.
 int stage_queries(QueryCache &qc, const Plan &plan, const char *queries, int nq, int qlen, int slen, cudaStream_t stream,
                   const void **d_tab) {
-    const size_t qbytes = (size_t)nq * (qlen + 1);
+    if (nq <= 0 || qlen <= 0) return fail(BGSA_ERR_ARG, "stage_queries: no queries");
+    const size_t qbytes = (size_t)nq * (size_t)(qlen + 1);
     std::vector<char> key(sizeof(Plan) + sizeof(int) * 3 + qbytes);
     memcpy(key.data(), &plan, sizeof(Plan));
     const int dims[3] = {nq, qlen, slen};

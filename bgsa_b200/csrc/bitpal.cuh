@@ -73,11 +73,12 @@ struct BitpalPacked {
     static constexpr int K = K_;
     static constexpr int A = S::A, B = S::B, NB = S::NB, NH = S::NH;
     static constexpr bool SEMI = MODE == BITPAL_SEMIGLOBAL;
+    static constexpr int kOpsPerWord = 65;
     static constexpr int E0 = SEMI ? -S::G : 0;              // e_{-1}: horizontal delta of the top row, minus G
     using Params = BitpalParams;
-    // cur/best/tword/tbit: semi-global only -- running S[m][t] - S[m][0], its maximum, and where this lane
-    // holds the last query row (tword < 0: it does not)
-    struct State { uint32_t d[NB][K]; int cur, best, tword, tbit; };
+    // semi-global only: tmask[j] = the bit of word j that is the last query row (0: not in this word),
+    // tbit its position, cur/best = running S[m][t] - S[m][0] and its maximum
+    struct State { uint32_t d[NB][K]; uint32_t tmask[SEMI ? K : 1]; int cur, best, tbit; bool owner; };
 
     static BGSA_HD void init(State &s, int first_bit, int qlen) {
 #pragma unroll
@@ -85,8 +86,12 @@ struct BitpalPacked {
 #pragma unroll
             for (int j = 0; j < K; j++) s.d[b][j] = 0u;      // first column: every vertical delta = G
         const int last = qlen - 1 - first_bit;
-        s.tword = (SEMI && last >= 0 && last < 32 * K) ? (last >> 5) : -1;
+        s.owner = SEMI && last >= 0 && last < 32 * K;
         s.tbit = last & 31;
+        if (SEMI) {
+#pragma unroll
+            for (int j = 0; j < K; j++) s.tmask[j] = (s.owner && (last >> 5) == j) ? (1u << s.tbit) : 0u;
+        }
         s.cur = 0; s.best = 0;
     }
 
@@ -117,21 +122,29 @@ struct BitpalPacked {
             const uint4 v = reinterpret_cast<const uint4 *>(row)[j];
             eq[4 * j] = v.x; eq[4 * j + 1] = v.y; eq[4 * j + 2] = v.z; eq[4 * j + 3] = v.w;
         }
-        // ---- decode the d classes the chains need: Z = [d == 0], D[v] = [d == v], v = 1..NH-1
+        // ---- decode the d classes the chains need: Z = [d == 0], D[v] = [d == v], v = 1..NH-1.
+        // Values below 4 share the test of the planes above bit 1 (one LOP3 each after that).
         uint32_t Z[K], remain[K];
         uint32_t D[NH > 1 ? NH : 1][K];
 #pragma unroll
         for (int j = 0; j < K; j++) {
-            uint32_t any = 0u;
+            uint32_t hiz = 0xffffffffu;                      // planes 2.. all zero  <=>  d < 4
 #pragma unroll
-            for (int b = 0; b < NB; b++) any |= s.d[b][j];
-            Z[j] = ~any;
+            for (int b = 2; b < NB; b++) hiz &= ~s.d[b][j];
+            const uint32_t d0 = s.d[0][j], d1 = NB > 1 ? s.d[1][j] : 0u;
+            Z[j] = lop3<LA & (0xFF ^ LB) & (0xFF ^ LC)>(hiz, d1, d0);
             remain[j] = Z[j] & ~eq[j];                       // d == 0 and mismatch: runs that propagate
 #pragma unroll
             for (int v = 1; v < NH; v++) {
-                uint32_t m = 0xffffffffu;
+                uint32_t m;
+                if (v == 1) m = lop3<LA & (0xFF ^ LB) & LC>(hiz, d1, d0);
+                else if (v == 2) m = lop3<LA & LB & (0xFF ^ LC)>(hiz, d1, d0);
+                else if (v == 3) m = lop3<LA & LB & LC>(hiz, d1, d0);
+                else {
+                    m = 0xffffffffu;
 #pragma unroll
-                for (int b = 0; b < NB; b++) m &= ((v >> b) & 1) ? s.d[b][j] : ~s.d[b][j];
+                    for (int b = NB - 1; b >= 0; b--) m &= ((v >> b) & 1) ? s.d[b][j] : ~s.d[b][j];
+                }
                 D[v][j] = m;
             }
         }
@@ -145,15 +158,15 @@ struct BitpalPacked {
             add_chain<K, CARRY>(sum, a0, Z);
             if (CARRY) out.push_cf();
 #pragma unroll
-            for (int j = 0; j < K; j++) Y[NH - 1][j] = (sum[j] ^ remain[j]) | eq[j];   // e_{p-1} == A, or match
+            for (int j = 0; j < K; j++) Y[NH - 1][j] = lop3<(LA ^ LB) | LC>(sum[j], remain[j], eq[j]);   // e_{p-1} == A, or match
 #pragma unroll
             for (int c = NH - 2; c >= 0; c--) {               // class k = B+1+c
                 uint32_t init[K], sh[K];
 #pragma unroll
                 for (int j = 0; j < K; j++) {
-                    uint32_t v = 0u;
+                    uint32_t v = D[1][j] & Y[c + 1][j];
 #pragma unroll
-                    for (int dl = 1; c + dl <= NH - 1; dl++) v |= D[dl][j] & Y[c + dl][j];
+                    for (int dl = 2; c + dl <= NH - 1; dl++) v = lop3<LA | (LB & LC)>(v, D[dl][j], Y[c + dl][j]);
                     init[j] = v;                              // e_p == k at a position with d != 0
                 }
                 const uint32_t sin = CARRY ? in.top() : (init_in(c) ? 0x80000000u : 0u);
@@ -163,11 +176,13 @@ struct BitpalPacked {
                 add_chain<K, CARRY>(sum, sh, remain);
                 if (CARRY) out.push_cf();
 #pragma unroll
-                for (int j = 0; j < K; j++) Y[c][j] = (sum[j] ^ remain[j]) & ~eq[j];
+                for (int j = 0; j < K; j++) Y[c][j] = lop3<(LA ^ LB) & (0xFF ^ LC)>(sum[j], remain[j], eq[j]);
             }
         }
         // ---- binary planes of y, then e = max(0, y - d), T = max(y, d), d' = T - (e << 1)
-        uint32_t e_prev[NB];
+        uint32_t e_prev[NB], e_last[NB];                     // e_last: the e planes at the last query row (one bit)
+#pragma unroll
+        for (int b = 0; b < NB; b++) e_last[b] = 0u;
 #pragma unroll
         for (int b = 0; b < NB; b++) e_prev[b] = CARRY ? in.top() : (((E0 >> b) & 1) ? 0x80000000u : 0u);   // top row
 #pragma unroll
@@ -184,26 +199,26 @@ struct BitpalPacked {
                 y[b] = v;
             }
             // borrow chain of y - d
+            // (explicit 3-input tables: left to itself the compiler materialises y ^ d and spends a third
+            //  instruction per plane)
+            constexpr int kBorrow = ((0xFF ^ LA) & LB) | ((0xFF ^ (LA ^ LB)) & LC);   // borrow out of a - b - c
             uint32_t diff[NB], br = 0u;
 #pragma unroll
             for (int b = 0; b < NB; b++) {
                 const uint32_t yb = y[b], db = s.d[b][j];
-                diff[b] = yb ^ db ^ br;
-                br = (~yb & db) | (~(yb ^ db) & br);
+                if (b == 0) { diff[b] = yb ^ db; br = ~yb & db; }
+                else { diff[b] = lop3<LA ^ LB ^ LC>(yb, db, br); br = lop3<kBorrow>(yb, db, br); }
             }
             const uint32_t lt = br;                           // y < d
             uint32_t e[NB], T[NB];
 #pragma unroll
             for (int b = 0; b < NB; b++) {
                 e[b] = diff[b] & ~lt;
-                T[b] = (lt & s.d[b][j]) | (~lt & y[b]);
+                T[b] = lop3<(LA & LB) | ((0xFF ^ LA) & LC)>(lt, s.d[b][j], y[b]);
             }
-            if (SEMI && j == s.tword) {                      // horizontal delta of the last query row
-                int v = 0;
+            if (SEMI) {                                      // branch-free: one LOP3 per plane and word
 #pragma unroll
-                for (int b = 0; b < NB; b++) v += (int)((e[b] >> s.tbit) & 1u) << b;
-                s.cur += v + S::G;
-                s.best = s.cur > s.best ? s.cur : s.best;
+                for (int b = 0; b < NB; b++) e_last[b] = lop3<LA | (LB & LC)>(e_last[b], e[b], s.tmask[SEMI ? j : 0]);
             }
             // shift e one position up (e_{p-1} aligned with p), then d' = T - es
             uint32_t br2 = 0u;
@@ -212,9 +227,16 @@ struct BitpalPacked {
                 const uint32_t es = shl1_carry(e_prev[b], e[b]);
                 e_prev[b] = e[b];
                 const uint32_t tb = T[b];
-                s.d[b][j] = tb ^ es ^ br2;
-                br2 = (~tb & es) | (~(tb ^ es) & br2);
+                if (b == 0) { s.d[b][j] = tb ^ es; br2 = ~tb & es; }
+                else { s.d[b][j] = lop3<LA ^ LB ^ LC>(tb, es, br2); if (b + 1 < NB) br2 = lop3<kBorrow>(tb, es, br2); }
             }
+        }
+        if (SEMI) {                                          // horizontal delta of the last query row = e + G
+            int v = 0;
+#pragma unroll
+            for (int b = 0; b < NB; b++) v += (int)(e_last[b] >> s.tbit) << b;
+            s.cur += v + S::G;                               // (lanes that do not own the row add G to a value nobody reads)
+            s.best = s.cur > s.best ? s.cur : s.best;
         }
         if (CARRY) {
 #pragma unroll
@@ -226,7 +248,7 @@ struct BitpalPacked {
     static BGSA_HD Partial partial(const State &s, int first_bit, int qlen) {
         Partial r; r.sum = 0; r.minpre = 0;
         if (SEMI) {                                          // only the lane with the last query row has the answer
-            r.minpre = s.tword >= 0 ? -s.best : 0x3fffffff;
+            r.minpre = s.owner ? -s.best : 0x3fffffff;
         } else {
 #pragma unroll
             for (int j = 0; j < K; j++) {
@@ -252,6 +274,7 @@ template <class S, int K_>
 struct BitpalNonPacked {
     static constexpr int K = K_;
     static constexpr int A = S::A, B = S::B, NH = S::NH;
+    static constexpr int kOpsPerWord = 185;
     using Params = BitpalParams;
     struct State { uint32_t d[A][K]; };        // d[v-1][j] = [d == v]
 

@@ -15,11 +15,10 @@
     X(20, 1) X(24, 1) X(32, 1) X(24, 2) X(32, 2) X(24, 4) X(32, 4) X(20, 8) X(24, 8) X(32, 8)  \
     X(24, 16) X(32, 16) X(24, 32) X(32, 32)
 
-// BitPAl packed
+// BitPAl packed (global and semi-global)
 #define BGSA_BITPAL_PACKED_INSTANCES(X)                                                      \
-    X(1, 1) X(2, 1) X(3, 1) X(4, 1) X(5, 1) X(6, 1) X(8, 1) X(10, 1) X(6, 2) X(8, 2) X(10, 2)  \
-    X(6, 4) X(8, 4) X(10, 4) X(6, 8) X(8, 8) X(10, 8) X(6, 16) X(8, 16) X(10, 16) X(5, 32)     \
-    X(6, 32) X(8, 32) X(10, 32)
+    X(1, 1) X(2, 1) X(3, 1) X(4, 1) X(5, 1) X(6, 1) X(8, 1) X(10, 1) X(6, 2) X(10, 2)         \
+    X(8, 4) X(10, 4) X(8, 8) X(10, 8) X(8, 16) X(10, 16) X(8, 32) X(10, 32)
 
 // BitPAl non-packed (one vector per delta value: register hungry, so few words per lane)
 #define BGSA_BITPAL_NONPACKED_INSTANCES(X)                                                   \

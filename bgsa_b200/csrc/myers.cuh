@@ -28,6 +28,7 @@ struct MyersParams { int sign; };              // -1: score = -distance (generat
 template <int K_, int MODE>
 struct MyersAlgo {
     static constexpr int K = K_;
+    static constexpr int kOpsPerWord = 10;
     using Params = MyersParams;
     struct State { uint32_t pv[K], mv[K]; };
     // carry stream (CarryIn/CarryOut, consumption order): add carry, Ph shift-in, Mh shift-in
