@@ -297,11 +297,16 @@ def main():
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     # roofline.traffic: DRAM bytes of the align kernel per launch, from the committed ncu --set full capture of the
     # same kernel (profiles/ncu_summary.json, written by tools/ncu_summarize.py), scaled to this launch's subjects
-    traffic = None
+    traffic, pipe_ncu = None, None
     try:
         prof = json.loads((ROOT / "profiles" / "ncu_summary.json").read_text()).get(args.workload, {})
         if "dram_bytes_per_subject" in prof:
             traffic = prof["dram_bytes_per_subject"] * ns
+        if "alu_pipe_pct" in prof:
+            # frac is measured against the survey's instruction MODEL; a kernel that needs fewer instructions per cell
+            # than the model reads above 1.0 while the pipe itself cannot exceed 100 % -- this is the pipe's own counter
+            pipe_ncu = {"alu_pipe_busy": prof["alu_pipe_pct"] / 100.0, "issue_slots_busy": prof["issue_active_pct"] / 100.0,
+                        "fma_pipe_busy": prof["fma_pipe_pct"] / 100.0, "kernel": prof.get("kernel"), "source": prof.get("source")}
     except (OSError, ValueError):
         pass
     line = {
@@ -314,7 +319,7 @@ def main():
                 "ms_per_step": 1e3 * e2e_s / args.steps, "api": "bgsa_align_batch (pinned host rows in, host scores out)"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "int_alu", "achieved": achieved / 1e12, "peak": int_peak / 1e12, "unit": "Tlane-op/s",
-                     "frac": achieved / int_peak, "traffic": traffic,
+                     "frac": achieved / int_peak, "traffic": traffic, "pipe_utilisation_ncu": pipe_ncu,
                      "kernel_ms": align_ms, "ops_per_cell_model": ops_cell,
                      "peak_source": "measured live: LOP3 issue-rate probe bgsa_int_peak (MEASURED_PEAKS.json has no integer peak); "
                                     "nominal 148 SM x 64 lanes x 1.965 GHz = 18.6",

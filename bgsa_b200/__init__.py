@@ -83,6 +83,8 @@ def load():
         "bgsa_align_batch_wait": (i32, [i32, i32]),
         "bgsa_malloc_host": (vp, [C.c_size_t]),
         "bgsa_free_host": (None, [vp]),
+        "bgsa_host_register": (i32, [vp, C.c_size_t]),
+        "bgsa_host_unregister": (i32, [vp]),
         "bgsa_packed_bytes": (i64, [i32, i64]),
         "bgsa_pack_subjects_device": (i32, [PP, vp, i32, i64, vp, i32, vp]),
         "bgsa_align_device": (i32, [PP, vp, i32, i32, vp, i32, i64, vp, i64, i32, vp]),
@@ -101,6 +103,7 @@ def load():
 EXPORTED_SYMBOLS = [
     "bgsa_version", "bgsa_last_error", "bgsa_device_count", "bgsa_params_default", "bgsa_result_size", "bgsa_supported",
     "bgsa_align_batch", "bgsa_align_batch_submit", "bgsa_align_batch_wait", "bgsa_malloc_host", "bgsa_free_host",
+    "bgsa_host_register", "bgsa_host_unregister",
     "bgsa_packed_bytes", "bgsa_pack_subjects_device", "bgsa_align_device", "bgsa_launch_count", "bgsa_kernel_name",
     "bgsa_int_peak", "bgsa_align_peq_chunk",
 ]

@@ -327,6 +327,16 @@ void *bgsa_malloc_host(size_t bytes) {
     return p;
 }
 void bgsa_free_host(void *p) { if (p) cudaFreeHost(p); }
+int bgsa_host_register(void *p, size_t bytes) {
+    if (!p || bytes == 0) return fail(BGSA_ERR_ARG, "bgsa_host_register: empty buffer");
+    CUDA_TRY(cudaHostRegister(p, bytes, cudaHostRegisterDefault));
+    return BGSA_OK;
+}
+int bgsa_host_unregister(void *p) {
+    if (!p) return fail(BGSA_ERR_ARG, "bgsa_host_unregister: NULL");
+    CUDA_TRY(cudaHostUnregister(p));
+    return BGSA_OK;
+}
 
 int64_t bgsa_packed_bytes(int subject_len, int64_t count) {
     if (subject_len <= 0 || count < 0) return -1;

@@ -103,6 +103,11 @@ int bgsa_align_batch_wait(int device, int slot);
 /* Pinned host memory for the buffers above (malloc_mem/free_mem, global.c:17-23). */
 void *bgsa_malloc_host(size_t bytes);
 void bgsa_free_host(void *p);
+/* Pin buffers the caller already owns (the reference allocates its read/result buffers once per run with
+ * malloc_mem, global.c:17-23, cal_cpu.c:258-267): page-locks [p, p+bytes) so that the copies of
+ * bgsa_align_batch run at PCIe speed and overlap the kernels.  Unregister before freeing the buffer. */
+int bgsa_host_register(void *p, size_t bytes);
+int bgsa_host_unregister(void *p);
 
 /* ---- device-resident entries (inputs already in HBM; used for kernel-only timing) ------ */
 /* Size in bytes of the packed form of `count` subjects of `subject_len` bases. */

@@ -332,3 +332,21 @@ def test_pack_kernels_bit_exact(B, slen, n, layout_algo):
             assert (codes == ec).all(), (variant, shift)
             assert ((flags != 0) == ef).all(), (variant, shift)
             assert (nm[ef] == en[ef]).all(), (variant, shift)      # the N plane is only defined for flagged tiles
+
+
+def test_host_register_pins_caller_buffers(B):
+    """bgsa_host_register: the integrator keeps its own (malloc'ed) buffers; results are unchanged."""
+    import ctypes as C
+    q, s = synth.make("C2", 70_000)
+    lib = B.load()
+    s2 = np.ascontiguousarray(s.copy())
+    out = np.zeros((1, s2.shape[0]), dtype=np.int16)
+    assert lib.bgsa_host_register(s2.ctypes.data, s2.nbytes) == 0
+    assert lib.bgsa_host_register(out.ctypes.data, out.nbytes) == 0
+    try:
+        got = B.align_batch(B.Params.default(B.BITPAL_PACKED), q, s2, out=out)
+    finally:
+        assert lib.bgsa_host_unregister(s2.ctypes.data) == 0
+        assert lib.bgsa_host_unregister(out.ctypes.data) == 0
+    assert (got == expect(3, q, s)).all()
+    assert lib.bgsa_host_register(None, 10) == 1          # BGSA_ERR_ARG
