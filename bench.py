@@ -203,6 +203,9 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     B.load()
+    # one process per GPU: allocate this rank's pinned buffers on the GPU's own NUMA node (BGSA_NO_NUMA_BIND=1 to skip)
+    numa_node = -1 if os.environ.get("BGSA_NO_NUMA_BIND") else B.bind_thread_to_device(local_rank)
+    config["host_numa_node"] = numa_node
     params = B.Params.default(wl["algo"], **wl["kw"])
     # every rank owns its own contiguous shard of equal size (weak scaling; no data-path collective)
     query, _ = synth.make(wl["cfg"], 1)

@@ -22,7 +22,7 @@ import numpy as np
 __all__ = [
     "MYERS_GLOBAL", "MYERS_SEMIGLOBAL", "BANDED_MYERS", "BITPAL_PACKED", "BITPAL_NONPACKED", "BITPAL_PACKED_SEMIGLOBAL",
     "BgsaError", "Params", "SeqT", "load", "lib_path", "align_batch", "result_dtype", "to_codes",
-    "packed_bytes", "pack_subjects_device", "align_device", "int_peak", "launch_count", "kernel_name", "supported",
+    "packed_bytes", "pack_subjects_device", "align_device", "int_peak", "bind_thread_to_device", "launch_count", "kernel_name", "supported",
 ]
 
 MYERS_GLOBAL, MYERS_SEMIGLOBAL, BANDED_MYERS, BITPAL_PACKED, BITPAL_NONPACKED, BITPAL_PACKED_SEMIGLOBAL = range(6)
@@ -85,6 +85,7 @@ def load():
         "bgsa_free_host": (None, [vp]),
         "bgsa_host_register": (i32, [vp, C.c_size_t]),
         "bgsa_host_unregister": (i32, [vp]),
+        "bgsa_bind_thread_to_device": (i32, [i32, C.POINTER(i32)]),
         "bgsa_packed_bytes": (i64, [i32, i64]),
         "bgsa_pack_subjects_device": (i32, [PP, vp, i32, i64, vp, i32, vp]),
         "bgsa_align_device": (i32, [PP, vp, i32, i32, vp, i32, i64, vp, i64, i32, vp]),
@@ -103,7 +104,7 @@ def load():
 EXPORTED_SYMBOLS = [
     "bgsa_version", "bgsa_last_error", "bgsa_device_count", "bgsa_params_default", "bgsa_result_size", "bgsa_supported",
     "bgsa_align_batch", "bgsa_align_batch_submit", "bgsa_align_batch_wait", "bgsa_malloc_host", "bgsa_free_host",
-    "bgsa_host_register", "bgsa_host_unregister",
+    "bgsa_host_register", "bgsa_host_unregister", "bgsa_bind_thread_to_device",
     "bgsa_packed_bytes", "bgsa_pack_subjects_device", "bgsa_align_device", "bgsa_launch_count", "bgsa_kernel_name",
     "bgsa_int_peak", "bgsa_align_peq_chunk",
 ]
@@ -182,6 +183,13 @@ def align_device(params: Params, queries: np.ndarray, d_packed_ptr: int, subject
     qc = np.ascontiguousarray(to_codes(np.asarray(queries, dtype=np.uint8)))
     _check(load().bgsa_align_device(C.byref(params), qc.ctypes.data, qc.shape[0], qc.shape[1] - 1, d_packed_ptr,
                                     subject_len, count, d_results_ptr, result_stride, device, stream))
+
+
+def bind_thread_to_device(device: int = 0) -> int:
+    """Pins the calling thread to the CPUs of the GPU's NUMA node; returns the node (-1: none exposed)."""
+    node = C.c_int(-1)
+    _check(load().bgsa_bind_thread_to_device(device, C.byref(node)))
+    return node.value
 
 
 def int_peak(device: int = 0):

@@ -2,8 +2,10 @@
 // contexts (streams + grow-only device buffers), host<->device staging and kernel selection.
 // No computation happens on the host besides building the query's match masks (5 x W words).
 #include <cuda_runtime.h>
+#include <sched.h>
 
 #include <atomic>
+#include <cctype>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -330,6 +332,42 @@ void bgsa_free_host(void *p) { if (p) cudaFreeHost(p); }
 int bgsa_host_register(void *p, size_t bytes) {
     if (!p || bytes == 0) return fail(BGSA_ERR_ARG, "bgsa_host_register: empty buffer");
     CUDA_TRY(cudaHostRegister(p, bytes, cudaHostRegisterDefault));
+    return BGSA_OK;
+}
+int bgsa_bind_thread_to_device(int device, int *numa_node) {
+    if (numa_node) *numa_node = -1;
+    char bus[32] = "";
+    CUDA_TRY(cudaDeviceGetPCIBusId(bus, sizeof(bus), device));
+    for (char *c = bus; *c; c++) *c = (char)tolower((unsigned char)*c);
+    char path[128];
+    snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/numa_node", bus);
+    FILE *f = fopen(path, "r");
+    int node = -1;
+    if (f) { if (fscanf(f, "%d", &node) != 1) node = -1; fclose(f); }
+    if (node < 0) return BGSA_OK;                       // no NUMA information: leave the thread alone
+    snprintf(path, sizeof(path), "/sys/devices/system/node/node%d/cpulist", node);
+    f = fopen(path, "r");
+    if (!f) return BGSA_OK;
+    cpu_set_t set;
+    CPU_ZERO(&set);
+    int a, b, n = 0;
+    while (fscanf(f, "%d", &a) == 1) {                   // "0-31,64-95"
+        b = a;
+        int ch = fgetc(f);
+        if (ch == '-') { if (fscanf(f, "%d", &b) != 1) b = a; ch = fgetc(f); }
+        for (int c = a; c <= b && c < CPU_SETSIZE; c++) { CPU_SET(c, &set); n++; }
+        if (ch != ',') break;
+    }
+    fclose(f);
+    if (n == 0) return BGSA_OK;
+    // keep only CPUs this process is allowed to use (containers); give up quietly if none is left
+    cpu_set_t allowed;
+    if (sched_getaffinity(0, sizeof(allowed), &allowed) == 0) {
+        CPU_AND(&set, &set, &allowed);
+        if (CPU_COUNT(&set) == 0) return BGSA_OK;
+    }
+    if (sched_setaffinity(0, sizeof(set), &set) != 0) return fail(BGSA_ERR_ARG, "sched_setaffinity failed for NUMA node %d", node);
+    if (numa_node) *numa_node = node;
     return BGSA_OK;
 }
 int bgsa_host_unregister(void *p) {

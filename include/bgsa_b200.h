@@ -108,6 +108,11 @@ void bgsa_free_host(void *p);
  * bgsa_align_batch run at PCIe speed and overlap the kernels.  Unregister before freeing the buffer. */
 int bgsa_host_register(void *p, size_t bytes);
 int bgsa_host_unregister(void *p);
+/* Binds the calling host thread to the CPUs of the NUMA node `device` hangs off (sysfs numa_node of its PCI
+ * function), so that host buffers allocated afterwards are local to the GPU that will read them -- with one
+ * process (or feeding thread) per GPU the 8 H2D streams of a box otherwise meet on one memory controller.
+ * *numa_node receives the node, or -1 when the platform exposes none (then nothing is changed).  Linux only. */
+int bgsa_bind_thread_to_device(int device, int *numa_node);
 
 /* ---- device-resident entries (inputs already in HBM; used for kernel-only timing) ------ */
 /* Size in bytes of the packed form of `count` subjects of `subject_len` bases. */
