@@ -83,7 +83,9 @@ static cudaError_t launch_pack_t(const uint8_t *rows, int slen, long long count,
     auto nmask = const_cast<uint32_t *>(v.nmask);
     auto flags = const_cast<uint8_t *>(v.tile_has_n);
     const int stride = slen + 1;
-    const size_t warp_bytes = sizeof(uint32_t) * (size_t)pack_warp_words(stride);
+    int G = pack_tiles_per_pass(stride);
+    while (G > 1 && sizeof(uint32_t) * (size_t)pack_warp_words(stride, G) > 12 * 1024) G--;   // keep >= 4 CTAs of 4 warps per SM
+    const size_t warp_bytes = sizeof(uint32_t) * (size_t)pack_warp_words(stride, G);
     constexpr size_t kSmemMax = 200 * 1024;
     static const bool simple_only = getenv("BGSA_PACK_SIMPLE") != nullptr;       // A/B knob
     if (stride < 16 || warp_bytes > kSmemMax || simple_only) {
@@ -106,10 +108,11 @@ static cudaError_t launch_pack_t(const uint8_t *rows, int slen, long long count,
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, warps * 32, smem);
     if (e != cudaSuccess) return e;
     if (occ < 1) occ = 1;
-    long long blocks = (v.ntiles + warps - 1) / warps;
+    const long long npasses = (v.ntiles + G - 1) / G;
+    long long blocks = (npasses + warps - 1) / warps;
     const long long cap = (long long)sm_count * occ;
     if (blocks > cap) blocks = cap;
-    kern<<<(unsigned)blocks, warps * 32, smem, stream>>>(rows, slen, count, codes, nmask, flags, v.ntiles, v.ku, v.kn);
+    kern<<<(unsigned)blocks, warps * 32, smem, stream>>>(rows, slen, count, codes, nmask, flags, v.ntiles, v.ku, v.kn, G);
     return cudaGetLastError();
 }
 

@@ -127,10 +127,13 @@ pack_kernel(const uint8_t *__restrict__ rows, int slen, long long count, uint4 *
 constexpr int kPackUnroll = 4;
 
 __host__ __device__ constexpr int pack_phys(int idx) { return idx + (idx >> 5); }   // one pad word per 32: kills bank conflicts of power-of-two row pitches
-// shared-memory words one warp needs for rows of `stride` bytes
-__host__ __device__ inline int pack_strip_pieces(int stride) { return 2 * stride + 3; }          // ceil((15 + 32*stride)/16) + 1
-__host__ __device__ inline int pack_code_words(int stride) { return pack_phys(pack_strip_pieces(stride) + 8) + 1; }
-__host__ __device__ inline int pack_warp_words(int stride) { return pack_code_words(stride) + (pack_strip_pieces(stride) + 8 + 1) / 2 + 1; }
+// shared-memory words one warp needs for a pass over `g` tiles of rows of `stride` bytes
+__host__ __device__ inline int pack_strip_pieces(int stride, int g) { return 2 * stride * g + 3; }   // ceil((15 + 32*g*stride)/16) + 1
+__host__ __device__ inline int pack_code_words(int stride, int g) { return pack_phys(pack_strip_pieces(stride, g) + 8) + 1; }
+__host__ __device__ inline int pack_warp_words(int stride, int g) { return pack_code_words(stride, g) + (pack_strip_pieces(stride, g) + 8 + 1) / 2 + 1; }
+// tiles per pass: short rows are grouped so that a pass holds ~1000 pieces (whole groups of 128 dominate, the
+// per-pass overhead is amortised) -- rows of 100 bases: 6 tiles, 150: 4, >= 512: 1
+__host__ __device__ inline int pack_tiles_per_pass(int stride) { const int g = (512 + stride - 1) / stride; return g < 1 ? 1 : (g > 8 ? 8 : g); }
 
 __device__ __forceinline__ uint32_t shl_clamp(uint32_t v, uint32_t n) {    // PTX shl clamps n > 31 to "all bits out"
     uint32_t d; asm("shl.b32 %0, %1, %2;" : "=r"(d) : "r"(v), "r"(n)); return d;
@@ -200,35 +203,42 @@ __device__ __forceinline__ uint32_t encode_piece(const uint4 v, int e, uint32_t 
 template <int LAYOUT>
 __global__ void __launch_bounds__(128)
 pack_stream_kernel(const uint8_t *__restrict__ rows, int slen, long long count, uint4 *__restrict__ codes,
-                   uint32_t *__restrict__ nmask, uint8_t *__restrict__ tile_has_n, long long ntiles, int ku, int kn) {
+                   uint32_t *__restrict__ nmask, uint8_t *__restrict__ tile_has_n, long long ntiles, int ku, int kn, int G) {
     extern __shared__ __align__(16) uint32_t s_pack[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
     const int stride = slen + 1;
-    uint32_t *s_c = s_pack + warp * pack_warp_words(stride);
-    uint16_t *s_n = reinterpret_cast<uint16_t *>(s_c + pack_code_words(stride));
+    uint32_t *s_c = s_pack + warp * pack_warp_words(stride, G);
+    uint16_t *s_n = reinterpret_cast<uint16_t *>(s_c + pack_code_words(stride, G));
     // tile starts are multiples of 32 bytes from `rows`: the misalignment of the run is the same for every tile
     const int off = (int)(reinterpret_cast<uintptr_t>(rows) & 15);
     const int inc = 512 % stride;                                   // advance of (position mod stride) per loop trip
     int m0 = (16 * lane - off) % stride;                            // position of this lane's first piece inside its row
     if (m0 < 0) m0 += stride;
-    const int base_pos = off + lane * stride;                       // strip position of this lane's own row
-    const int wi0 = base_pos >> 4, sub = base_pos & 15;
+    const long long npasses = (ntiles + G - 1) / G;
 
-    for (long long tile = (long long)blockIdx.x * warps + warp; tile < ntiles; tile += (long long)gridDim.x * warps) {
-        const long long first = tile * kTileSubjects;
-        const int live_rows = (int)min((long long)kTileSubjects, count - first);
+    // one pass = G consecutive tiles = one contiguous run of up to 32*G rows
+    for (long long pass = (long long)blockIdx.x * warps + warp; pass < npasses; pass += (long long)gridDim.x * warps) {
+        const long long tile0 = pass * G;
+        const long long first = tile0 * kTileSubjects;
+        const int pass_rows = (int)min((long long)kTileSubjects * G, count - first);
         const uint4 *src = reinterpret_cast<const uint4 *>(rows + first * stride - off);
-        const int npieces = (off + live_rows * stride + 15) >> 4;
+        const int npieces = (off + pass_rows * stride + 15) >> 4;
         // ---- step 1: stream order.  Whole groups of kPackUnroll x 32 pieces first (no bounds checks, loads in
         // flight before the first is used), then the remainder one piece per lane and trip.
         uint32_t any_n = 0u;
         int m = m0;
         const int full = npieces - npieces % (32 * kPackUnroll);
         int p0 = lane;
-        for (; p0 < full; p0 += 32 * kPackUnroll) {
-            uint4 v[kPackUnroll];
+        uint4 v[kPackUnroll], nv[kPackUnroll];                      // current / next group (software prefetch)
+        if (p0 < full) {
 #pragma unroll
             for (int k = 0; k < kPackUnroll; k++) v[k] = __ldg(src + p0 + 32 * k);
+        }
+        for (; p0 < full; p0 += 32 * kPackUnroll) {
+            if (p0 + 32 * kPackUnroll < full) {                      // warp-uniform
+#pragma unroll
+                for (int k = 0; k < kPackUnroll; k++) nv[k] = __ldg(src + p0 + 32 * kPackUnroll + 32 * k);
+            }
             const int ph = pack_phys(p0);                           // pack_phys(p0 + 32k) = ph + 33k
             uint32_t redo = 0u;                                     // bit k: piece k needs the exact path
 #pragma unroll
@@ -250,6 +260,8 @@ pack_stream_kernel(const uint8_t *__restrict__ rows, int slen, long long count, 
                 s_n[p] = (uint16_t)r.y;
                 any_n |= r.y;
             }
+#pragma unroll
+            for (int k = 0; k < kPackUnroll; k++) v[k] = nv[k];
         }
         uint32_t redo_tail = 0u;                                    // bit i: tail piece p0 + 32 i needs the exact path
         for (int p = p0, i = 0; p < npieces; p += 32, i++) {
@@ -269,55 +281,68 @@ pack_stream_kernel(const uint8_t *__restrict__ rows, int slen, long long count, 
             s_n[p] = (uint16_t)r.y;
             any_n |= r.y;
         }
-        const bool tile_n = __ballot_sync(0xffffffffu, any_n != 0u) != 0u;
+        const bool pass_n = __ballot_sync(0xffffffffu, any_n != 0u) != 0u;
         __syncwarp();
-        // ---- step 2: subject order
-        const bool live = lane < live_rows;
-        for (int u = 0; u < ku; u++) {
-            uint4 outv = make_uint4(0u, 0u, 0u, 0u);
-            if (live) {
-                uint32_t t[5];
-#pragma unroll
-                for (int i = 0; i < 5; i++) t[i] = s_c[pack_phys(wi0 + 4 * u + i)];
-                if (LAYOUT == LAYOUT_CODES) {
-                    const int sh = 2 * sub;
-                    outv.x = __funnelshift_r(t[0], t[1], sh); outv.y = __funnelshift_r(t[1], t[2], sh);
-                    outv.z = __funnelshift_r(t[2], t[3], sh); outv.w = __funnelshift_r(t[3], t[4], sh);
-                    const int nb = slen - u * kBasesPerUnit;          // bases of this unit that exist
-                    if (nb < kBasesPerUnit) {
-                        auto keep = [](int n) { return n >= 16 ? 0xffffffffu : (n <= 0 ? 0u : ((1u << (2 * n)) - 1u)); };
-                        outv.x &= keep(nb); outv.y &= keep(nb - 16); outv.z &= keep(nb - 32); outv.w &= keep(nb - 48);
-                    }
-                } else {
-                    // strip word = lo16 | hi16 << 16 per 16 bases
-                    const uint32_t lo01 = prmt(t[0], t[1], 0x5410u), lo23 = prmt(t[2], t[3], 0x5410u);
-                    const uint32_t hi01 = prmt(t[0], t[1], 0x7632u), hi23 = prmt(t[2], t[3], 0x7632u);
-                    outv.x = __funnelshift_r(lo01, lo23, sub); outv.y = __funnelshift_r(hi01, hi23, sub);
-                    outv.z = __funnelshift_r(lo23, t[4] & 0xffffu, sub); outv.w = __funnelshift_r(hi23, t[4] >> 16, sub);
-                    const int nb = slen - u * kBasesPerUnit;
-                    if (nb < kBasesPerUnit) {
-                        auto keep = [](int n) { return n >= 32 ? 0xffffffffu : (n <= 0 ? 0u : ((1u << n) - 1u)); };
-                        outv.x &= keep(nb); outv.y &= keep(nb); outv.z &= keep(nb - 32); outv.w &= keep(nb - 32);
-                    }
-                }
-            }
-            codes[(tile * ku + u) * 32 + lane] = outv;
-        }
-        if (tile_n) {
-            for (int k = 0; k < kn; k++) {
-                uint32_t nm = 0u;
+        // ---- step 2: subject order, tile by tile
+        for (int g = 0; g < G; g++) {
+            const long long tile = tile0 + g;
+            if (tile >= ntiles) break;
+            const int base_pos = off + (g * kTileSubjects + lane) * stride;   // strip position of this lane's own row
+            const int wi0 = base_pos >> 4, sub = base_pos & 15;
+            const bool live = g * kTileSubjects + lane < pass_rows;
+            for (int u = 0; u < ku; u++) {
+                uint4 outv = make_uint4(0u, 0u, 0u, 0u);
                 if (live) {
-                    const int q = wi0 + 2 * k;
-                    const uint32_t a = (uint32_t)s_n[q] | ((uint32_t)s_n[q + 1] << 16), b = s_n[q + 2];
-                    nm = __funnelshift_r(a, b, sub);
-                    const int nb = slen - 32 * k;
-                    if (nb < 32) nm &= (1u << nb) - 1u;
+                    uint32_t t[5];
+#pragma unroll
+                    for (int i = 0; i < 5; i++) t[i] = s_c[pack_phys(wi0 + 4 * u + i)];
+                    if (LAYOUT == LAYOUT_CODES) {
+                        const int sh = 2 * sub;
+                        outv.x = __funnelshift_r(t[0], t[1], sh); outv.y = __funnelshift_r(t[1], t[2], sh);
+                        outv.z = __funnelshift_r(t[2], t[3], sh); outv.w = __funnelshift_r(t[3], t[4], sh);
+                        const int nb = slen - u * kBasesPerUnit;          // bases of this unit that exist
+                        if (nb < kBasesPerUnit) {
+                            auto keep = [](int n) { return n >= 16 ? 0xffffffffu : (n <= 0 ? 0u : ((1u << (2 * n)) - 1u)); };
+                            outv.x &= keep(nb); outv.y &= keep(nb - 16); outv.z &= keep(nb - 32); outv.w &= keep(nb - 48);
+                        }
+                    } else {
+                        // strip word = lo16 | hi16 << 16 per 16 bases
+                        const uint32_t lo01 = prmt(t[0], t[1], 0x5410u), lo23 = prmt(t[2], t[3], 0x5410u);
+                        const uint32_t hi01 = prmt(t[0], t[1], 0x7632u), hi23 = prmt(t[2], t[3], 0x7632u);
+                        outv.x = __funnelshift_r(lo01, lo23, sub); outv.y = __funnelshift_r(hi01, hi23, sub);
+                        outv.z = __funnelshift_r(lo23, t[4] & 0xffffu, sub); outv.w = __funnelshift_r(hi23, t[4] >> 16, sub);
+                        const int nb = slen - u * kBasesPerUnit;
+                        if (nb < kBasesPerUnit) {
+                            auto keep = [](int n) { return n >= 32 ? 0xffffffffu : (n <= 0 ? 0u : ((1u << n) - 1u)); };
+                            outv.x &= keep(nb); outv.y &= keep(nb); outv.z &= keep(nb - 32); outv.w &= keep(nb - 32);
+                        }
+                    }
                 }
-                nmask[(tile * kn + k) * 32 + lane] = nm;
+                codes[(tile * ku + u) * 32 + lane] = outv;
             }
+            // N plane: only for tiles that really hold an 'N' (rare: decided per tile, the pass flag only says "look")
+            bool flag = false;
+            if (pass_n) {
+                auto nword = [&](int k) {
+                    uint32_t nm = 0u;
+                    if (live) {
+                        const int q = wi0 + 2 * k;
+                        const uint32_t a = (uint32_t)s_n[q] | ((uint32_t)s_n[q + 1] << 16), b = s_n[q + 2];
+                        nm = __funnelshift_r(a, b, sub);
+                        const int nb = slen - 32 * k;
+                        if (nb < 32) nm &= (1u << nb) - 1u;
+                    }
+                    return nm;
+                };
+                uint32_t row_n = 0u;
+                for (int k = 0; k < kn; k++) row_n |= nword(k);
+                flag = __ballot_sync(0xffffffffu, row_n != 0u) != 0u;
+                if (flag)
+                    for (int k = 0; k < kn; k++) nmask[(tile * kn + k) * 32 + lane] = nword(k);
+            }
+            if (lane == 0) tile_has_n[tile] = flag ? 1 : 0;
         }
-        if (lane == 0) tile_has_n[tile] = tile_n ? 1 : 0;
-        __syncwarp();      // the strip is rewritten by the next tile
+        __syncwarp();      // the strip is rewritten by the next pass
     }
 }
 
