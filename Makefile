@@ -13,10 +13,21 @@ LIB      ?= bgsa_b200/libbgsa_b200.so
 
 HDRS := $(wildcard $(CSRC)/*.cuh $(CSRC)/*.h) include/bgsa_b200.h
 
-OBJS := $(BUILD)/api.o $(BUILD)/inst_misc.o $(BUILD)/inst_myers_g.o $(BUILD)/inst_myers_s.o \
-        $(BUILD)/inst_bp_p0.o $(BUILD)/inst_bp_p1.o $(BUILD)/inst_bp_p2.o \
-        $(BUILD)/inst_bp_n0.o $(BUILD)/inst_bp_n1.o $(BUILD)/inst_bp_n2.o \
-        $(BUILD)/inst_bp_s0.o $(BUILD)/inst_bp_s1.o $(BUILD)/inst_bp_s2.o
+# Scoring schemes compiled into the library ("match,mismatch,gap", scheme id = position).  The reference runs its Java
+# generator once per scheme (generator/.../Main.java:240-315); here a scheme is a set of template instances:
+#     make SCHEMES="2,-3,-5 1,-1,-1 1,-3,-2 3,-2,-4"
+# The first three are the default and are what instances.h falls back to when BGSA_SCHEMES is not defined.
+SCHEMES  ?= 2,-3,-5 1,-1,-1 1,-3,-2
+comma    := ,
+SCHEME_IDS := $(shell i=0; for s in $(SCHEMES); do echo $$i; i=$$((i+1)); done)
+scheme_of = $(word $(shell echo $$(($(1)+1))),$(SCHEMES))
+SCHEME_LIST := $(foreach i,$(SCHEME_IDS),X($(i)$(comma) $(subst $(comma),$(comma) ,$(call scheme_of,$(i)))))
+# (nvcc splits -D values at commas, so the list travels in a generated header)
+SCHEME_HDR := $(BUILD)/bgsa_schemes.h
+SCHEME_DEF := -include $(SCHEME_HDR)
+
+BP_OBJS := $(foreach i,$(SCHEME_IDS),$(BUILD)/inst_bp_p$(i).o $(BUILD)/inst_bp_n$(i).o $(BUILD)/inst_bp_s$(i).o)
+OBJS := $(BUILD)/api.o $(BUILD)/inst_misc.o $(BUILD)/inst_myers_g.o $(BUILD)/inst_myers_s.o $(BP_OBJS)
 
 .PHONY: all lib tools sim clean
 all: lib tools sim
@@ -25,39 +36,30 @@ lib: $(LIB)
 $(LIB): $(OBJS)
 	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -lcudart
 
-$(BUILD)/api.o: $(CSRC)/api.cu $(HDRS) | $(BUILD)
-	$(NVCC) $(NVFLAGS) -c $< -o $@
-$(BUILD)/inst_misc.o: $(CSRC)/inst_misc.cu $(HDRS) | $(BUILD)
-	$(NVCC) $(NVFLAGS) -c $< -o $@
+$(SCHEME_HDR): Makefile | $(BUILD)
+	@echo '#define BGSA_SCHEMES(X) $(SCHEME_LIST)' > $@.tmp; cmp -s $@.tmp $@ || mv $@.tmp $@; rm -f $@.tmp
+.PHONY: FORCE
+$(SCHEME_HDR): FORCE
+
+$(BUILD)/api.o: $(CSRC)/api.cu $(HDRS) $(SCHEME_HDR) | $(BUILD)
+	$(NVCC) $(NVFLAGS) $(SCHEME_DEF) -c $< -o $@
+$(BUILD)/inst_misc.o: $(CSRC)/inst_misc.cu $(HDRS) $(SCHEME_HDR) | $(BUILD)
+	$(NVCC) $(NVFLAGS) $(SCHEME_DEF) -c $< -o $@
 $(BUILD)/inst_myers_g.o: $(CSRC)/inst_myers.cu $(HDRS) | $(BUILD)
 	$(NVCC) $(NVFLAGS) -DBGSA_MYERS_MODE=0 -c $< -o $@
 $(BUILD)/inst_myers_s.o: $(CSRC)/inst_myers.cu $(HDRS) | $(BUILD)
 	$(NVCC) $(NVFLAGS) -DBGSA_MYERS_MODE=1 -c $< -o $@
-# BitPAl: one object per (scheme id, variant: p packed, n non-packed, s packed semi-global) -- keep in sync with BGSA_SCHEMES in instances.h
-$(BUILD)/inst_bp_p0.o: $(CSRC)/inst_bitpal.cu $(HDRS) | $(BUILD)
-	$(NVCC) $(NVFLAGS) -DBGSA_SCHEME_ID=0 -DBGSA_M=2 -DBGSA_I=-3 -DBGSA_G=-5 -DBGSA_PACKED=1 -c $< -o $@
-$(BUILD)/inst_bp_p1.o: $(CSRC)/inst_bitpal.cu $(HDRS) | $(BUILD)
-	$(NVCC) $(NVFLAGS) -DBGSA_SCHEME_ID=1 -DBGSA_M=1 -DBGSA_I=-1 -DBGSA_G=-1 -DBGSA_PACKED=1 -c $< -o $@
-$(BUILD)/inst_bp_p2.o: $(CSRC)/inst_bitpal.cu $(HDRS) | $(BUILD)
-	$(NVCC) $(NVFLAGS) -DBGSA_SCHEME_ID=2 -DBGSA_M=1 -DBGSA_I=-3 -DBGSA_G=-2 -DBGSA_PACKED=1 -c $< -o $@
-$(BUILD)/inst_bp_n0.o: $(CSRC)/inst_bitpal.cu $(HDRS) | $(BUILD)
-	$(NVCC) $(NVFLAGS) -DBGSA_SCHEME_ID=0 -DBGSA_M=2 -DBGSA_I=-3 -DBGSA_G=-5 -DBGSA_PACKED=0 -c $< -o $@
-$(BUILD)/inst_bp_n1.o: $(CSRC)/inst_bitpal.cu $(HDRS) | $(BUILD)
-	$(NVCC) $(NVFLAGS) -DBGSA_SCHEME_ID=1 -DBGSA_M=1 -DBGSA_I=-1 -DBGSA_G=-1 -DBGSA_PACKED=0 -c $< -o $@
-$(BUILD)/inst_bp_n2.o: $(CSRC)/inst_bitpal.cu $(HDRS) | $(BUILD)
-	$(NVCC) $(NVFLAGS) -DBGSA_SCHEME_ID=2 -DBGSA_M=1 -DBGSA_I=-3 -DBGSA_G=-2 -DBGSA_PACKED=0 -c $< -o $@
-
-$(BUILD)/inst_bp_s0.o: $(CSRC)/inst_bitpal.cu $(HDRS) | $(BUILD)
-	$(NVCC) $(NVFLAGS) -DBGSA_SCHEME_ID=0 -DBGSA_M=2 -DBGSA_I=-3 -DBGSA_G=-5 -DBGSA_PACKED=2 -c $< -o $@
-$(BUILD)/inst_bp_s1.o: $(CSRC)/inst_bitpal.cu $(HDRS) | $(BUILD)
-	$(NVCC) $(NVFLAGS) -DBGSA_SCHEME_ID=1 -DBGSA_M=1 -DBGSA_I=-1 -DBGSA_G=-1 -DBGSA_PACKED=2 -c $< -o $@
-$(BUILD)/inst_bp_s2.o: $(CSRC)/inst_bitpal.cu $(HDRS) | $(BUILD)
-	$(NVCC) $(NVFLAGS) -DBGSA_SCHEME_ID=2 -DBGSA_M=1 -DBGSA_I=-3 -DBGSA_G=-2 -DBGSA_PACKED=2 -c $< -o $@
+# BitPAl: one object per (scheme id, variant: p packed = 1, n non-packed = 0, s packed semi-global = 2)
+define BP_RULE
+$$(BUILD)/inst_bp_$(2)$(1).o: $$(CSRC)/inst_bitpal.cu $$(HDRS) | $$(BUILD)
+	$$(NVCC) $$(NVFLAGS) -DBGSA_SCHEME_ID=$(1) -DBGSA_M=$(word 1,$(subst $(comma), ,$(call scheme_of,$(1)))) -DBGSA_I=$(word 2,$(subst $(comma), ,$(call scheme_of,$(1)))) -DBGSA_G=$(word 3,$(subst $(comma), ,$(call scheme_of,$(1)))) -DBGSA_PACKED=$(3) -c $$< -o $$@
+endef
+$(foreach i,$(SCHEME_IDS),$(eval $(call BP_RULE,$(i),p,1))$(eval $(call BP_RULE,$(i),n,0))$(eval $(call BP_RULE,$(i),s,2)))
 
 # test-only: the DP column functions compiled for the HOST (no GPU needed), see tests/host_sim.cu
 sim: tests/libhost_sim.so
-tests/libhost_sim.so: tests/host_sim.cu $(HDRS)
-	$(NVCC) -O2 -std=c++17 -Xcompiler -fPIC -shared -I$(CSRC) -o $@ $<
+tests/libhost_sim.so: tests/host_sim.cu $(HDRS) $(SCHEME_HDR)
+	$(NVCC) -O2 -std=c++17 -Xcompiler -fPIC -shared -I$(CSRC) $(SCHEME_DEF) -o $@ $<
 
 SHIMS := myers_cpu semiglobal_cpu banded_cpu myers_sse bitpal_avx2 bitpal_avx512
 SHIM_LIBS := $(foreach v,$(SHIMS),bgsa_b200/libalign_core_$(v).so)

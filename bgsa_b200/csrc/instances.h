@@ -26,4 +26,7 @@
 
 // Scoring schemes (match, mismatch, gap) with a kernel instance; index = scheme id.
 // Scheme 0 is the one the reference checks in (original/BGSA_AVX512/align_core.c:13-15).
+// The Makefile passes the list (make SCHEMES="2,-3,-5 ..."); this is its default.
+#ifndef BGSA_SCHEMES
 #define BGSA_SCHEMES(X) X(0, 2, -3, -5) X(1, 1, -1, -1) X(2, 1, -3, -2)
+#endif

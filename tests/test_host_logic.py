@@ -152,6 +152,36 @@ def test_bitpal_semiglobal_columns_on_host(sim, scheme, mig):
             assert (got == R.dp_scores("nw_semi", q, s, M=M, I=I, G=G).astype(np.int16)).all(), (K, L, ql, sl)
 
 
+def test_other_scoring_schemes_match_dp(tmp_path):
+    """`make SCHEMES=...` = re-running the reference's generator for another (M, I, G): the same sources
+    instantiated for five more schemes (common factor 2, zero match score, -G in a high class, ...) on the host
+    simulator against plain DP -- packed global, packed semi-global and non-packed."""
+    import subprocess
+    schemes = [(3, -2, -4), (4, -6, -10), (1, -1, -2), (5, -3, -4), (0, -1, -1)]
+    hdr = tmp_path / "schemes.h"
+    hdr.write_text("#define BGSA_SCHEMES(X) " + " ".join(f"X({i}, {m}, {x}, {g})" for i, (m, x, g) in enumerate(schemes)) + "\n")
+    so = tmp_path / "libhost_sim_schemes.so"
+    subprocess.check_call(["nvcc", "-O1", "-std=c++17", "-Xcompiler", "-fPIC", "-shared", "-I", str(ROOT / "bgsa_b200" / "csrc"),
+                           "-include", str(hdr), "-o", str(so), str(ROOT / "tests" / "host_sim.cu")],
+                          stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    lib = C.CDLL(str(so))
+    lib.host_sim_align.restype = C.c_int
+    lib.host_sim_align.argtypes = [C.c_int] * 5 + [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p]
+    rng = np.random.default_rng(77)
+    for sid, (M, I, G) in enumerate(schemes):
+        for K, L, algo, kind in [(5, 1, 3, "nw"), (6, 2, 3, "nw"), (10, 2, 5, "nw_semi"), (3, 1, 5, "nw_semi"), (2, 2, 4, "nw")]:
+            ql = min(32 * K * L, 260) - int(rng.integers(0, 20))
+            sl = int(rng.integers(ql // 2, ql + 60))
+            q = R.random_rows(rng, 1, ql, with_n=0.02)
+            s = R.random_rows(rng, 4, sl, with_n=0.02)
+            s[0, : min(ql, sl)] = q[0, : min(ql, sl)]
+            if sl > ql + 5:
+                s[1, 3:3 + ql] = q[0, :ql]
+            rc, got = run_sim(lib, algo, sid, K, L, q, s)
+            assert rc == 0
+            assert (got == R.dp_scores(kind, q, s, M=M, I=I, G=G).astype(np.int16)).all(), ((M, I, G), K, L, algo)
+
+
 def test_shard_counts():
     from bgsa_b200.sharding import shard_counts, shard_range
     assert shard_counts(1_000_000, 8) == [124992] * 7 + [125056]
