@@ -75,6 +75,7 @@ def load():
         "bgsa_version": (C.c_char_p, []),
         "bgsa_last_error": (C.c_char_p, []),
         "bgsa_device_count": (i32, [C.POINTER(i32)]),
+        "bgsa_init_devices": (i32, [i32]),
         "bgsa_params_default": (None, [PP, i32]),
         "bgsa_result_size": (i32, [i32]),
         "bgsa_supported": (i32, [PP, i32, i32]),
@@ -102,7 +103,7 @@ def load():
 
 
 EXPORTED_SYMBOLS = [
-    "bgsa_version", "bgsa_last_error", "bgsa_device_count", "bgsa_params_default", "bgsa_result_size", "bgsa_supported",
+    "bgsa_version", "bgsa_last_error", "bgsa_device_count", "bgsa_init_devices", "bgsa_params_default", "bgsa_result_size", "bgsa_supported",
     "bgsa_align_batch", "bgsa_align_batch_submit", "bgsa_align_batch_wait", "bgsa_malloc_host", "bgsa_free_host",
     "bgsa_host_register", "bgsa_host_unregister", "bgsa_bind_thread_to_device",
     "bgsa_packed_bytes", "bgsa_pack_subjects_device", "bgsa_align_device", "bgsa_launch_count", "bgsa_kernel_name",

@@ -11,6 +11,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/bgsa_b200.h"
@@ -284,6 +286,31 @@ const char *bgsa_last_error(void) { return g_err; }
 int bgsa_device_count(int *count) {
     if (!count) return fail(BGSA_ERR_ARG, "count is NULL");
     CUDA_TRY(cudaGetDeviceCount(count));
+    return BGSA_OK;
+}
+
+int bgsa_init_devices(int n_devices) {
+    int have = 0;
+    CUDA_TRY(cudaGetDeviceCount(&have));
+    if (n_devices < 1 || n_devices > have || n_devices > kMaxDevices)
+        return fail(BGSA_ERR_ARG, "bgsa_init_devices: %d devices requested, %d present", n_devices, have);
+    std::vector<int> rc((size_t)n_devices, BGSA_OK);
+    std::vector<std::string> msg((size_t)n_devices);
+    std::vector<std::thread> th;
+    for (int g = 0; g < n_devices; g++)
+        th.emplace_back([g, &rc, &msg] {
+            DeviceCtx *ctx;
+            if (cudaSetDevice(g) != cudaSuccess || cudaFree(nullptr) != cudaSuccess) {   // creates the primary context
+                rc[(size_t)g] = BGSA_ERR_CUDA;
+                msg[(size_t)g] = cudaGetErrorString(cudaGetLastError());
+                return;
+            }
+            rc[(size_t)g] = get_ctx(g, &ctx);                  // streams, events (short, under the registry lock)
+            if (rc[(size_t)g] != BGSA_OK) msg[(size_t)g] = g_err;   // g_err is thread-local
+        });
+    for (std::thread &t : th) t.join();
+    for (int g = 0; g < n_devices; g++)
+        if (rc[(size_t)g] != BGSA_OK) return fail(rc[(size_t)g], "device %d: %s", g, msg[(size_t)g].c_str());
     return BGSA_OK;
 }
 

@@ -96,14 +96,12 @@ static cudaError_t launch_pack_t(const uint8_t *rows, int slen, long long count,
         return cudaGetLastError();
     }
     auto kern = pack_stream_kernel<LAYOUT>;
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax);
-        if (e != cudaSuccess) return e;
-        attr_done = true;
-    }
     const int warps = 4 * warp_bytes <= 96 * 1024 ? 4 : (2 * warp_bytes <= kSmemMax ? 2 : 1);
     const size_t smem = warp_bytes * warps;
+    if (smem > 48 * 1024) {   // opt-in above 48 KB is a per-device (per-context) function attribute: set it wherever we launch
+        cudaError_t ea = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax);
+        if (ea != cudaSuccess) return ea;
+    }
     int occ = 0;
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, warps * 32, smem);
     if (e != cudaSuccess) return e;

@@ -75,9 +75,9 @@ int main(int argc, char **argv) {
     bgsa_params_t prm;
     bgsa_params_default(&prm, BGSA_MYERS_GLOBAL);
     int algo = BGSA_MYERS_GLOBAL, ngpu = 1, have_k = 0;
-    int M = 2, I = -3, G = -5, sign = -1, threshold = 31;
+    int M = 2, I = -3, G = -5, sign = -1, threshold = 31, verbose = 0;
     int c;
-    while ((c = getopt(argc, argv, "t:q:d:f:n:N:R:Dk:a:M:I:G:m:g:")) != -1) {
+    while ((c = getopt(argc, argv, "t:q:d:f:n:N:R:Dk:a:M:I:G:m:g:v")) != -1) {
         switch (c) {
             case 'q': file_query = optarg; break;
             case 'd': file_database = optarg; break;
@@ -98,6 +98,7 @@ int main(int argc, char **argv) {
             case 'G': G = atoi(optarg); break;
             case 'm': sign = atoi(optarg) == 0 ? -1 : 1; break;
             case 'g': ngpu = atoi(optarg); break;
+            case 'v': verbose = 1; break;
             default: print_help();
         }
     }
@@ -113,7 +114,17 @@ int main(int argc, char **argv) {
 
     double total_start = now_s(), read_total_time = 0, write_total_time = 0, cal_total_time = 0;
     int devcount = 0;
+    double init_time = now_s(), alloc_time = 0;
+    /* Driver start-up grows with the number of GPUs it has to bring up (seconds on an 8-GPU box): unless the user
+     * chose the devices, expose only the -g we are going to use. */
+    if (!getenv("CUDA_VISIBLE_DEVICES")) {
+        char vis[8 * MAX_GPUS] = "";
+        for (int g = 0; g < ngpu; g++) snprintf(vis + strlen(vis), sizeof(vis) - strlen(vis), g ? ",%d" : "%d", g);
+        setenv("CUDA_VISIBLE_DEVICES", vis, 1);
+    }
     if (bgsa_device_count(&devcount) != BGSA_OK || devcount < ngpu) die("Error - CUDA devices unavailable: %s", bgsa_last_error());
+    if (bgsa_init_devices(ngpu) != BGSA_OK) die("Error - %s", bgsa_last_error());   /* all contexts at once, not one after the other */
+    init_time = now_s() - init_time;
 
     char info_name[4096];
     snprintf(info_name, sizeof(info_name), "%s.info", file_result);                /* main.c:80-87 */
@@ -164,11 +175,13 @@ int main(int argc, char **argv) {
     /* ---- pinned ping-pong buffers (read_seq_a/b, align_results_a/b; cal_cpu.c:219-267) */
     char *rows_buf[2];
     void *res_buf[2];
+    alloc_time = now_s();
     for (int b = 0; b < 2; b++) {
         rows_buf[b] = (char *)bgsa_malloc_host((size_t)(rows_per_bucket * stride + 64));
         res_buf[b] = bgsa_malloc_host((size_t)esize * (size_t)ref_bucket_count * (size_t)rows_per_bucket + 64);
         if (!rows_buf[b] || !res_buf[b]) die("Error - %s", bgsa_last_error());
     }
+    alloc_time = now_s() - alloc_time;
 
     int64_t total_subjects = 0, rows_done = 0;
     int64_t next_rows = rows_per_bucket < total_rows ? rows_per_bucket : total_rows;
@@ -230,9 +243,11 @@ int main(int argc, char **argv) {
         total_subjects += rows;
     }
     fclose(fp_ref); fclose(fp_read); fclose(fp_result); fclose(fp_info);
+    double free_time = now_s();
     for (int b = 0; b < 2; b++) { bgsa_free_host(rows_buf[b]); bgsa_free_host(res_buf[b]); }
     free(ref);
     double total_end = now_s();
+    free_time = total_end - free_time;
 
     /* the reference's statistics block (cal_cpu.c:459-475); cal time includes H2D/D2H here */
     printf("score is %d, %d, %d\n", prm.match, prm.mismatch, prm.gap);
@@ -250,5 +265,7 @@ int main(int argc, char **argv) {
     printf("cal GCUPS is %.2f\n", 1.0 * ref_len * ref_count * read_len * total_subjects / cal_total_time / 1000000000);
     printf("Total GCUPS is %.2f\n", 1.0 * ref_len * ref_count * read_len * total_subjects / (total_end - total_start) / 1000000000);
     printf("\n\n");
+    if (verbose)   /* additive: where the wall time outside read/cal/write goes */
+        printf("gpu_init_time is %.3fs\nhost_alloc_time is %.3fs\nhost_free_time is %.3fs\n", init_time, alloc_time, free_time);
     return 0;
 }

@@ -74,6 +74,10 @@ typedef struct bgsa_seq_t {
 const char *bgsa_version(void);
 const char *bgsa_last_error(void);                  /* thread-local, never NULL                  */
 int bgsa_device_count(int *count);
+/* Creates the CUDA contexts, streams and per-device state of devices 0 .. n_devices-1 IN PARALLEL (one host thread
+ * per device).  Optional: every entry point initialises its device on first use, but context creation costs
+ * 0.3-1 s per GPU and a multi-GPU caller (aligner -g 8) would otherwise pay it eight times in a row. */
+int bgsa_init_devices(int n_devices);
 void bgsa_params_default(bgsa_params_t *p, int algo); /* 2/-3/-5, threshold 31, sign -1          */
 /* bytes per score: 1 for BGSA_BANDED_MYERS (common_write_t int8_t, banded/BGSA_CPU/config.h:21),
  * else 2 (int16_t, original/BGSA_CPU/config.h:19). */

@@ -136,6 +136,12 @@ def test_aligner_two_gpus_device_major_file(tmp_path):
     run([REF / "convert_int16", "-r", "two.bin", "-o", "two.txt"], tmp_path)
     txt = np.loadtxt(tmp_path / "two.txt", dtype=np.int64).reshape(3, -1)
     assert (txt == R.oracle_batch(R.ALGO_BITPAL_PACKED, q, s)).all()
+    # long rows on the second device too (the pack kernel opts in to > 48 KB of shared memory per device)
+    q5, s5 = synth.make("C5", 300)
+    R.write_rows(tmp_path / "q5.txt", q5); R.write_rows(tmp_path / "s5.txt", s5)
+    run([ALIGNER, "-a", "bitpal", "-g", "2", "-q", "q5.txt", "-d", "s5.txt", "-f", "two5.bin"], tmp_path)
+    got = np.fromfile(tmp_path / "two5.bin", dtype=np.int16)
+    assert (got[None, :] == R.oracle_batch(R.ALGO_BITPAL_PACKED, q5, s5)).all()
 
 
 # ---- the reference's own, unmodified host pipeline on top of our align_core shims -----------------
