@@ -350,3 +350,29 @@ def test_host_register_pins_caller_buffers(B):
         assert lib.bgsa_host_unregister(out.ctypes.data) == 0
     assert (got == expect(3, q, s)).all()
     assert lib.bgsa_host_register(None, 10) == 1          # BGSA_ERR_ARG
+
+
+def test_seeded_fuzz_all_algorithms(B):
+    """80 seeded random (query length, subject length, count, N rate) cases per algorithm family against the
+    oracle: odd lengths, counts off the tile/pass/chunk grids, lengths around every instance boundary."""
+    rng = np.random.default_rng(2026)
+    edges = [31, 32, 33, 63, 64, 65, 95, 96, 97, 159, 160, 161, 191, 192, 193, 255, 256, 257, 319, 320, 321, 383, 385, 639, 641]
+    for case in range(80):
+        ql = int(rng.choice(edges)) if case % 3 == 0 else int(rng.integers(1, 700))
+        sl = int(rng.choice(edges)) if case % 5 == 0 else int(rng.integers(1, 700))
+        ns = int(rng.integers(1, 400))
+        q = R.random_rows(rng, int(rng.integers(1, 4)), ql, with_n=float(rng.choice([0.0, 0.01, 0.2])))
+        s = R.random_rows(rng, ns, sl, with_n=float(rng.choice([0.0, 0.0, 0.02])))
+        k = min(ql, sl)
+        s[: ns // 2, :k] = q[0, :k]
+        for algo, oalgo in ((B.MYERS_GLOBAL, 0), (B.MYERS_SEMIGLOBAL, 1), (B.BITPAL_PACKED, 3), (B.BITPAL_PACKED_SEMIGLOBAL, 5)):
+            got = B.align_batch(B.Params.default(algo), q, s)
+            assert (got == R.oracle_batch(oalgo, q, s)).all(), (case, algo, ql, sl, ns)
+        if case % 4 == 0:
+            assert (B.align_batch(B.Params.default(B.BITPAL_NONPACKED), q, s) == R.oracle_batch(3, q, s)).all(), (case, ql, sl, ns)
+        e = int(rng.integers(1, 16))
+        if sl >= 20 and ((sl - 1) // 64 + 1) < ((sl - e + 63) // 64 + 1):     # banded: equal lengths, reference in bounds
+            qb = R.random_rows(rng, 1, sl)
+            sb = np.concatenate([R.mutate_rows(rng, qb[0, :sl], ns, 2 * e), R.random_rows(rng, 7, sl)])
+            got = B.align_batch(B.Params.default(B.BANDED_MYERS, threshold=e), qb, sb)
+            assert (got == R.oracle_batch(R.ALGO_BANDED, qb, sb, e=e)).all(), (case, "banded", sl, e)
