@@ -376,3 +376,39 @@ def test_seeded_fuzz_all_algorithms(B):
             sb = np.concatenate([R.mutate_rows(rng, qb[0, :sl], ns, 2 * e), R.random_rows(rng, 7, sl)])
             got = B.align_batch(B.Params.default(B.BANDED_MYERS, threshold=e), qb, sb)
             assert (got == R.oracle_batch(R.ALGO_BANDED, qb, sb, e=e)).all(), (case, "banded", sl, e)
+
+
+def test_two_slots_in_flight(B):
+    """bgsa_align_batch_submit/_wait: two jobs (slot 0 and 1, the reference's a/b ping-pong buffers, thread.c:35-170)
+    queued back to back on one device with different algorithms and pinned buffers from bgsa_malloc_host."""
+    import ctypes as C
+    lib = B.load()
+    rng = np.random.default_rng(12)
+    qa = R.random_rows(rng, 2, 150); sa = R.random_rows(rng, 50_000, 150)
+    qb = R.random_rows(rng, 1, 300); sb = R.random_rows(rng, 20_011, 260, with_n=0.01)
+
+    def pinned_copy(arr):
+        ptr = lib.bgsa_malloc_host(arr.nbytes)
+        assert ptr
+        buf = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), shape=(arr.nbytes,))
+        buf[:] = arr.reshape(-1).view(np.uint8)
+        return ptr, buf
+
+    pa, ba = pinned_copy(sa); pb, bb = pinned_copy(sb)
+    ra_ptr = lib.bgsa_malloc_host(2 * 2 * sa.shape[0]); rb_ptr = lib.bgsa_malloc_host(2 * sb.shape[0])
+    try:
+        seq_a = B.SeqT(150, sa.nbytes, sa.shape[0], 0, 0, pa); seq_b = B.SeqT(260, sb.nbytes, sb.shape[0], 0, 0, pb)
+        qca = np.ascontiguousarray(B.to_codes(qa)); qcb = np.ascontiguousarray(B.to_codes(qb))
+        p_a = B.Params.default(B.BITPAL_PACKED); p_b = B.Params.default(B.MYERS_SEMIGLOBAL)
+        assert lib.bgsa_align_batch_submit(C.byref(p_a), qca.ctypes.data, 2, 150, C.byref(seq_a), 0, sa.shape[0], ra_ptr, sa.shape[0], 0, 0) == 0
+        assert lib.bgsa_align_batch_submit(C.byref(p_b), qcb.ctypes.data, 1, 300, C.byref(seq_b), 11, sb.shape[0] - 11, rb_ptr, sb.shape[0] - 11, 0, 1) == 0
+        assert lib.bgsa_align_batch_wait(0, 1) == 0
+        assert lib.bgsa_align_batch_wait(0, 0) == 0
+        ra = np.ctypeslib.as_array(C.cast(ra_ptr, C.POINTER(C.c_int16)), shape=(2, sa.shape[0])).copy()
+        rb = np.ctypeslib.as_array(C.cast(rb_ptr, C.POINTER(C.c_int16)), shape=(1, sb.shape[0] - 11)).copy()
+        assert lib.bgsa_align_batch_wait(0, 2) == 1 and lib.bgsa_align_batch_submit(C.byref(p_a), qca.ctypes.data, 2, 150, C.byref(seq_a), 0, 1, ra_ptr, 1, 0, 2) == 1
+    finally:
+        for p in (pa, pb, ra_ptr, rb_ptr):
+            lib.bgsa_free_host(p)
+    assert (ra == R.oracle_batch(R.ALGO_BITPAL_PACKED, qa, sa)).all()
+    assert (rb == R.oracle_batch(R.ALGO_MYERS_SEMIGLOBAL, qb, sb[11:])).all()
