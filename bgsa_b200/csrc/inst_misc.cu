@@ -83,10 +83,19 @@ static cudaError_t launch_pack_t(const uint8_t *rows, int slen, long long count,
     auto nmask = const_cast<uint32_t *>(v.nmask);
     auto flags = const_cast<uint8_t *>(v.tile_has_n);
     const int stride = slen + 1;
+    constexpr size_t kSmemMax = 200 * 1024;
+    // tiles per warp pass: as many as make the passes long (short rows), but never so many that a small launch (one
+    // chunk of the batch pipeline) leaves warp slots idle -- keep at least ~2 passes per resident warp
     int G = pack_tiles_per_pass(stride);
     while (G > 1 && sizeof(uint32_t) * (size_t)pack_warp_words(stride, G) > 12 * 1024) G--;   // keep >= 4 CTAs of 4 warps per SM
+    {
+        const long long resident_warps = (long long)sm_count * 28;
+        const long long by_work = v.ntiles / (2 * resident_warps);
+        if (G > by_work) G = by_work < 1 ? 1 : (int)by_work;
+        static const char *force_g = getenv("BGSA_PACK_G");                                   // A/B knob
+        if (force_g && atoi(force_g) >= 1 && sizeof(uint32_t) * (size_t)pack_warp_words(stride, atoi(force_g)) <= kSmemMax / 4) G = atoi(force_g);
+    }
     const size_t warp_bytes = sizeof(uint32_t) * (size_t)pack_warp_words(stride, G);
-    constexpr size_t kSmemMax = 200 * 1024;
     static const bool simple_only = getenv("BGSA_PACK_SIMPLE") != nullptr;       // A/B knob
     if (stride < 16 || warp_bytes > kSmemMax || simple_only) {
         long long blocks = (v.ntiles + 3) / 4;
