@@ -52,7 +52,7 @@ __host__ __device__ constexpr int peq_row_stride(int k, int lanes) { return peq_
 
 template <class Algo, int L, int CH, int THREADS, int UNROLL>
 __global__ void __launch_bounds__(THREADS, BGSA_MIN_BLOCKS)
-align_kernel(PackedSubjects ps, const uint32_t *__restrict__ g_peq, int qlen, int16_t *__restrict__ results,
+align_kernel(PackedSubjects ps, const uint32_t *__restrict__ g_peq, int n_queries, int qlen, int16_t *__restrict__ results,
              long long result_stride, typename Algo::Params prm, unsigned long long *__restrict__ counters) {
     constexpr int K = Algo::K;
     constexpr int KP = peq_kp(K);
@@ -63,34 +63,45 @@ align_kernel(PackedSubjects ps, const uint32_t *__restrict__ g_peq, int qlen, in
     __shared__ __align__(16) uint32_t s_peq[kPeqRows * STRIDE];
     __shared__ __align__(128) uint4 s_stage[WARPS * 2 * CH * 32];
     __shared__ __align__(8) uint64_t s_bar[WARPS * 2];
+    __shared__ int s_skip;
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int rank = lane % L, group = lane / L;
-    const int q = blockIdx.y;
-    for (int i = threadIdx.x; i < kPeqRows * STRIDE; i += THREADS)
-        s_peq[i] = g_peq[(size_t)q * kPeqRows * STRIDE + i];
     WarpStage<CH> st;
     st.init(s_stage + warp * 2 * CH * 32, s_bar + warp * 2, lane);
-    __syncthreads();
 
     const uint32_t *my_peq = s_peq + rank * KP;
-    unsigned long long *counter = counters + q;
-    int16_t *out = results + (long long)q * result_stride;
     const int slen = ps.slen, ku = ps.ku;
     const int nstages = (ku + CH - 1) / CH;
-
-    // work unit = (tile, pass): the 32/L subjects of a tile that a warp has in flight at once.  Every warp starts
-    // on "its own" unit (static), further units come from the global counter: the next unit is claimed one unit
-    // ahead (its first stage is prefetched), and with a purely dynamic start the first warps to arrive would claim
-    // two units each while others get none whenever a launch holds about one unit per warp (chunked batches).
+    // work unit = (tile, pass): the 32/L subjects of a tile that a warp has in flight at once
     const long long nunits = ps.ntiles * L;
-    const long long total_warps = (long long)gridDim.x * WARPS;
-    long long unit = (long long)blockIdx.x * WARPS + warp;
     int sb = 0;
-    if (unit < nunits) st.issue(0, ps.codes + (unit / L) * ku * 32, min(CH, ku), lane);
+
+    // Many queries (the reference's buckets of up to 100, cal_cpu.c:210-216): the CTAs are dealt over the queries
+    // round-robin (CTA c starts on query c % n_queries) and, when their query runs out of work, move on to the next
+    // ones -- every resident CTA stays busy until the whole launch is done, whatever n_queries is.
+    for (int visit = 0; visit < n_queries; visit++) {
+    const int q = (int)((blockIdx.x + (unsigned)visit) % (unsigned)n_queries);
+    unsigned long long *counter = counters + q;
+    // Every warp of a CTA that STARTS on q has "its own" first unit (static), all further units come from the query's
+    // counter: the next unit is claimed one ahead (its first stage is prefetched), and with a purely dynamic start
+    // the first warps to arrive would claim two units each while others get none whenever a launch holds about
+    // one unit per warp (chunked batches).
+    const long long static_units = (long long)(gridDim.x / n_queries + (q < (int)(gridDim.x % n_queries) ? 1 : 0)) * WARPS;
+    __syncthreads();                                 // everybody is done with the previous query's masks
+    if (threadIdx.x == 0)
+        s_skip = visit > 0 && static_units + (long long)*reinterpret_cast<volatile unsigned long long *>(counter) >= nunits;
+    __syncthreads();
+    if (s_skip) continue;                            // (a stale read only costs a useless visit)
+    for (int i = threadIdx.x; i < kPeqRows * STRIDE; i += THREADS)
+        s_peq[i] = g_peq[(size_t)q * kPeqRows * STRIDE + i];
+    __syncthreads();
+    int16_t *out = results + (long long)q * result_stride;
+    long long unit = visit == 0 ? (long long)(blockIdx.x / n_queries) * WARPS + warp : static_units + next_tile(counter, lane);
+    if (unit < nunits) st.issue(sb, ps.codes + (unit / L) * ku * 32, min(CH, ku), lane);
 
     while (unit < nunits) {
-        const long long nxt = total_warps + next_tile(counter, lane);
+        const long long nxt = static_units + next_tile(counter, lane);
         const long long tile = unit / L;
         const int pass = (int)(unit % L);
         const bool with_n = ps.tile_has_n[tile] != 0;
@@ -197,6 +208,7 @@ align_kernel(PackedSubjects ps, const uint32_t *__restrict__ g_peq, int qlen, in
         }
         unit = nxt;
     }
+    }   // visit
 }
 
 }  // namespace bgsa

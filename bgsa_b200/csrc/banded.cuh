@@ -45,20 +45,23 @@ template <> struct BandWord<true> { using type = uint64_t; };
 // z = low bits of bases 32..63, w = high bits of bases 32..63.
 template <bool WIDE, int THREADS>
 __global__ void __launch_bounds__(THREADS)
-banded_kernel(PackedSubjects ps, const BandedRow *__restrict__ g_rows, int qlen, int e,
+banded_kernel(PackedSubjects ps, const BandedRow *__restrict__ g_rows, int n_queries, int qlen, int e,
               int8_t *__restrict__ results, long long result_stride, unsigned long long *__restrict__ counters) {
     using T = typename BandWord<WIDE>::type;
     const int lane = threadIdx.x & 31;
-    const int q = blockIdx.y;
-    const BandedRow *rows = g_rows + (size_t)q * qlen;
-    unsigned long long *counter = counters + q;
-    int8_t *out = results + (long long)q * result_stride;
     const int ku = ps.ku;
     const int sh = e + 1;                                     // plane index u = i + e + 1
     const int C = qlen <= 64 ? qlen : max(64, qlen - e);      // rows done at the last checkpoint
     const int max_err = 2 * e + 1;                            // threshold + h_threshold + 1 (:114)
 
-    for (long long tile = next_tile(counter, lane); tile < ps.ntiles; tile = next_tile(counter, lane)) {
+    // work unit = (query, tile), query-major, from ONE counter: the per-row masks of a query are read straight from
+    // global memory (uniform loads), so a warp changes query for free and every warp stays busy whatever n_queries is
+    const long long nwork = ps.ntiles * n_queries;
+    for (long long work = next_tile(counters, lane); work < nwork; work = next_tile(counters, lane)) {
+        const int q = n_queries == 1 ? 0 : (int)(work / ps.ntiles);
+        const long long tile = work - (long long)q * ps.ntiles;
+        const BandedRow *rows = g_rows + (size_t)q * qlen;
+        int8_t *out = results + (long long)q * result_stride;
         const bool with_n = ps.tile_has_n[tile] != 0;
         const uint4 *src = ps.codes + tile * ku * 32 + lane;
         const uint32_t *nsrc = ps.nmask + tile * ps.kn * 32 + lane;

@@ -58,14 +58,13 @@ static cudaError_t launch_banded_t(const LaunchArgs &a, const void *d_rows_table
     }
     cudaError_t err = cudaMemsetAsync(a.d_counters, 0, sizeof(unsigned long long) * a.n_queries, a.stream);
     if (err != cudaSuccess) return err;
-    long long want = (a.ps.ntiles + 3) / 4;
-    long long resident = (long long)a.sm_count * occ / (a.n_queries > 0 ? a.n_queries : 1);
-    if (resident < 1) resident = 1;
+    const int nq = a.n_queries > 0 ? a.n_queries : 1;
+    long long want = (a.ps.ntiles * nq + 3) / 4;
+    const long long resident = (long long)a.sm_count * occ;
     if (want > resident) want = resident;
     if (want < 1) want = 1;
-    dim3 grid((unsigned)want, (unsigned)a.n_queries);
-    kern<<<grid, THREADS, 0, a.stream>>>(a.ps, static_cast<const BandedRow *>(d_rows_table), a.qlen, e,
-                                         static_cast<int8_t *>(a.d_results), a.result_stride, a.d_counters);
+    kern<<<(unsigned)want, THREADS, 0, a.stream>>>(a.ps, static_cast<const BandedRow *>(d_rows_table), nq, a.qlen, e,
+                                                   static_cast<int8_t *>(a.d_results), a.result_stride, a.d_counters);
     return cudaGetLastError();
 }
 cudaError_t launch_banded(const LaunchArgs &a, const void *d_rows_table, int e) {

@@ -40,14 +40,13 @@ cudaError_t launch_align(const LaunchArgs &a, typename Algo::Params prm) {
     cudaError_t e = cudaMemsetAsync(a.d_counters, 0, sizeof(unsigned long long) * a.n_queries, a.stream);
     if (e != cudaSuccess) return e;
     const long long warps_per_cta = kAlignThreads / 32;
-    long long want = (a.ps.ntiles * L + warps_per_cta - 1) / warps_per_cta;   // one (tile, pass) work unit per warp at least
-    long long resident = (long long)a.sm_count * occ / (a.n_queries > 0 ? a.n_queries : 1);
-    if (resident < 1) resident = 1;
+    const int nq = a.n_queries > 0 ? a.n_queries : 1;
+    long long want = (a.ps.ntiles * L * nq + warps_per_cta - 1) / warps_per_cta;   // one (query, tile, pass) work unit per warp at least
+    const long long resident = (long long)a.sm_count * occ;
     if (want > resident) want = resident;
     if (want < 1) want = 1;
-    dim3 grid((unsigned)want, (unsigned)a.n_queries);
-    kern<<<grid, kAlignThreads, 0, a.stream>>>(a.ps, a.d_peq, a.qlen, static_cast<int16_t *>(a.d_results),
-                                               a.result_stride, prm, a.d_counters);
+    kern<<<(unsigned)want, kAlignThreads, 0, a.stream>>>(a.ps, a.d_peq, nq, a.qlen, static_cast<int16_t *>(a.d_results),
+                                                         a.result_stride, prm, a.d_counters);
     return cudaGetLastError();
 }
 
