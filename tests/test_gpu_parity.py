@@ -412,3 +412,21 @@ def test_two_slots_in_flight(B):
             lib.bgsa_free_host(p)
     assert (ra == R.oracle_batch(R.ALGO_BITPAL_PACKED, qa, sa)).all()
     assert (rb == R.oracle_batch(R.ALGO_MYERS_SEMIGLOBAL, qb, sb[11:])).all()
+
+
+@pytest.mark.parametrize("nq,ns", [(300, 70), (7, 5000), (101, 1), (1000, 33)])
+def test_query_counts_beyond_the_grid(B, nq, ns):
+    """More queries than CTAs, queries nobody starts on, one subject: the CTAs' walk over the queries must
+    visit every (query, tile) exactly once."""
+    rng = np.random.default_rng(nq * 31 + ns)
+    q = R.random_rows(rng, nq, 90, with_n=0.01)
+    s = R.random_rows(rng, ns, 75, with_n=0.01)
+    for algo, oalgo in ((B.MYERS_GLOBAL, 0), (B.BITPAL_PACKED, 3), (B.MYERS_SEMIGLOBAL, 1)):
+        assert (B.align_batch(B.Params.default(algo), q, s) == R.oracle_batch(oalgo, q, s)).all(), (algo, nq, ns)
+    qb = R.random_rows(rng, nq, 80)
+    sb = np.concatenate([R.mutate_rows(rng, qb[0, :80], ns, 10), R.random_rows(rng, 5, 80)])
+    got = B.align_batch(B.Params.default(B.BANDED_MYERS, threshold=5), qb, sb)
+    assert (got == R.oracle_batch(R.ALGO_BANDED, qb, sb, e=5)).all()
+    if nq == 300:    # a wavefront instance as well (L > 1)
+        ql = R.random_rows(rng, 40, 700); sl = R.random_rows(rng, 50, 200)
+        assert (B.align_batch(B.Params.default(B.BITPAL_PACKED), ql, sl) == R.oracle_batch(3, ql, sl)).all()
