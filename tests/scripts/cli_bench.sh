@@ -1,5 +1,6 @@
 #!/bin/bash
-# End-to-end CLI comparison on files (run under gpurun): our aligner vs the reference's aligner on the same
+# TEST INFRASTRUCTURE (runs the reference binaries of oracle/_ref as the checker).
+# End-to-end CLI comparison on files (run under gpurun: bash tests/scripts/cli_bench.sh <out>): our aligner vs the reference's aligner on the same
 # synthetic C2 / C3 files, byte-compare of the result files, wall times.
 set -u
 OUT=gpurun_out/${1:-cli}

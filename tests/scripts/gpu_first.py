@@ -1,8 +1,8 @@
 """First GPU contact: parity of every algorithm against the oracle on small inputs + rough timings."""
 import sys, time, ctypes as C
 from pathlib import Path
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent.parent))
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
-sys.path.insert(0, str(Path(__file__).resolve().parent.parent / "tests"))
 import numpy as np
 import torch
 import bgsa_b200 as B

@@ -2,7 +2,7 @@
 nq queries x ns subjects through the host-buffer API and the device-resident API."""
 import sys, time
 from pathlib import Path
-sys.path.insert(0, str(Path(__file__).resolve().parent.parent)); sys.path.insert(0, str(Path(__file__).resolve().parent.parent / "tests"))
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent.parent)); sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 import numpy as np, torch
 import bgsa_b200 as B, refutil as R
 

@@ -1,8 +1,8 @@
 """Small end-to-end run of every algorithm (host-buffer API + device-resident API) for compute-sanitizer:
-    compute-sanitizer --tool memcheck python tools/sanitize_small.py"""
+    compute-sanitizer --tool memcheck python tests/scripts/sanitize_small.py"""
 import sys
 from pathlib import Path
-sys.path.insert(0, str(Path(__file__).resolve().parent.parent)); sys.path.insert(0, str(Path(__file__).resolve().parent.parent / "tests"))
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent.parent)); sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 import numpy as np, torch
 import bgsa_b200 as B, refutil as R
 
