@@ -43,8 +43,12 @@ template <> struct BandWord<true> { using type = uint64_t; };
 
 // planes layout of a 128-bit unit: x = low bits of bases 0..31, y = high bits of bases 0..31,
 // z = low bits of bases 32..63, w = high bits of bases 32..63.
-template <bool WIDE, int THREADS>
-__global__ void __launch_bounds__(THREADS)
+// (min-blocks: 10 CTAs of 128 threads = 48 registers for the narrow band -- what the kernel needs; left alone ptxas
+//  takes 61 and the occupancy drops to 8)
+// MULTI = false (one query): the row-mask table and the result row are kernel-wide constants (uniform-register
+// addressing); MULTI = true: they change with the work unit's query.
+template <bool WIDE, bool MULTI, int THREADS>
+__global__ void __launch_bounds__(THREADS, WIDE ? 8 : 10)
 banded_kernel(PackedSubjects ps, const BandedRow *__restrict__ g_rows, int n_queries, int qlen, int e,
               int8_t *__restrict__ results, long long result_stride, unsigned long long *__restrict__ counters) {
     using T = typename BandWord<WIDE>::type;
@@ -58,10 +62,10 @@ banded_kernel(PackedSubjects ps, const BandedRow *__restrict__ g_rows, int n_que
     // global memory (uniform loads), so a warp changes query for free and every warp stays busy whatever n_queries is
     const long long nwork = ps.ntiles * n_queries;
     for (long long work = next_tile(counters, lane); work < nwork; work = next_tile(counters, lane)) {
-        const int q = n_queries == 1 ? 0 : (int)(work / ps.ntiles);
+        const int q = MULTI ? (int)(work / ps.ntiles) : 0;
         const long long tile = work - (long long)q * ps.ntiles;
-        const BandedRow *rows = g_rows + (size_t)q * qlen;
-        int8_t *out = results + (long long)q * result_stride;
+        const BandedRow *rows = MULTI ? g_rows + (size_t)q * qlen : g_rows;
+        int8_t *out = MULTI ? results + (long long)q * result_stride : results;
         const bool with_n = ps.tile_has_n[tile] != 0;
         const uint4 *src = ps.codes + tile * ku * 32 + lane;
         const uint32_t *nsrc = ps.nmask + tile * ps.kn * 32 + lane;

@@ -312,8 +312,10 @@ struct BitpalNonPacked {
         // DV(v, j) = [d_p == v]
 #define DV(v, j) (((v) == 0) ? Z[j] : s.d[((v) > 0 ? (v) : 1) - 1][j])
         // X[v][j] = [e_{p-1} == v] for v = 1..A (shifted form), built class by class.
-        // [y_p == v]: v == A -> X[A] | match ; B < v < A -> X[v] & ~match ; v == B -> rest.
+        // Yh[v][j] = [y_p == v]: v == A -> X[A] | match ; B < v < A -> X[v] & ~match ; v == B -> rest.
+        // (every OR-of-ANDs below is written as one LOP3 per term: a | (b & c))
         uint32_t X[A + 1][K];
+        uint32_t Yh[A + 1][K];
         {
             uint32_t a0[K], sum[K];
 #pragma unroll
@@ -322,15 +324,18 @@ struct BitpalNonPacked {
             add_chain<K, CARRY>(sum, a0, Z);
             if (CARRY) out.push_cf();
 #pragma unroll
-            for (int j = 0; j < K; j++) X[A][j] = sum[j] ^ remain[j];
+            for (int j = 0; j < K; j++) {
+                X[A][j] = sum[j] ^ remain[j];
+                Yh[A][j] = lop3<(LA ^ LB) | LC>(sum[j], remain[j], eq[j]);
+            }
 #pragma unroll
             for (int k = A - 1; k > B; k--) {
                 uint32_t init[K], sh[K];
 #pragma unroll
                 for (int j = 0; j < K; j++) {
-                    uint32_t v = DV(A - k, j) & (X[A][j] | eq[j]);
+                    uint32_t v = DV(A - k, j) & Yh[A][j];
 #pragma unroll
-                    for (int h = A - 1; h > k; h--) v |= DV(h - k, j) & (X[h][j] & ~eq[j]);
+                    for (int h = A - 1; h > k; h--) v = lop3<LA | (LB & LC)>(v, DV(h - k, j), Yh[h][j]);
                     init[j] = v;
                 }
                 const uint32_t sin = CARRY ? in.top() : 0u;
@@ -340,13 +345,16 @@ struct BitpalNonPacked {
                 add_chain<K, CARRY>(sum, sh, remain);
                 if (CARRY) out.push_cf();
 #pragma unroll
-                for (int j = 0; j < K; j++) X[k][j] = sum[j] ^ remain[j];
+                for (int j = 0; j < K; j++) {
+                    X[k][j] = sum[j] ^ remain[j];
+                    Yh[k][j] = lop3<(LA ^ LB) & (0xFF ^ LC)>(sum[j], remain[j], eq[j]);
+                }
             }
         }
         uint32_t rest[K];
 #pragma unroll
         for (int j = 0; j < K; j++) {
-            uint32_t any = X[A][j] | eq[j];
+            uint32_t any = Yh[A][j];
 #pragma unroll
             for (int k = A - 1; k > B; k--) any |= X[k][j];
             rest[j] = ~any;
@@ -357,11 +365,10 @@ struct BitpalNonPacked {
             uint32_t init[K];
 #pragma unroll
             for (int j = 0; j < K; j++) {
-                uint32_t v = DV(A - k, j) & (X[A][j] | eq[j]);
+                uint32_t v = DV(A - k, j) & Yh[A][j];
 #pragma unroll
-                for (int h = A - 1; h > B; h--) v |= DV(h - k, j) & (X[h][j] & ~eq[j]);
-                v |= DV(B - k, j) & rest[j];
-                init[j] = v;
+                for (int h = A - 1; h > B; h--) v = lop3<LA | (LB & LC)>(v, DV(h - k, j), Yh[h][j]);
+                init[j] = lop3<LA | (LB & LC)>(v, DV(B - k, j), rest[j]);
             }
             const uint32_t sin = CARRY ? in.top() : 0u;
             if (CARRY) out.push_top(init[K - 1]);
@@ -394,7 +401,8 @@ struct BitpalNonPacked {
             for (int k = 1; k <= A; k++) {
                 uint32_t v = 0u;
 #pragma unroll
-                for (int m = (k > B ? k : B); m <= A; m++) v |= mx[m] & ((m - k) == 0 ? X0[j] : X[(m - k) > 0 ? (m - k) : 1][j]);
+                for (int m = (k > B ? k : B); m <= A; m++)
+                    v = lop3<LA | (LB & LC)>(v, mx[m], (m - k) == 0 ? X0[j] : X[(m - k) > 0 ? (m - k) : 1][j]);
                 nd[k - 1] = v;
             }
 #pragma unroll

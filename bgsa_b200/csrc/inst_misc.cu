@@ -45,7 +45,8 @@ cudaError_t launch_bitpal_nonpacked(int scheme, int K, int L, const LaunchArgs &
 template <bool WIDE>
 static cudaError_t launch_banded_t(const LaunchArgs &a, const void *d_rows_table, int e) {
     constexpr int THREADS = 128;
-    auto kern = banded_kernel<WIDE, THREADS>;
+    const bool multi = a.n_queries > 1;
+    auto kern = multi ? banded_kernel<WIDE, true, THREADS> : banded_kernel<WIDE, false, THREADS>;
     static int occ = 0;
     if (occ == 0) {
         cudaError_t err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, 0);
