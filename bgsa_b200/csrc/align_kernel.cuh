@@ -24,11 +24,12 @@
 //            K-word work; the price is L-1 idle steps per subject (< 1 % for the long sequences
 //            this mode is for).
 //
-// Launch geometry: grid = (persistent CTAs, n_queries), THREADS threads.  Shared memory holds the
-// query's Peq (5 rows) once per CTA and, per warp, a 2-stage buffer of subject tiles filled by
-// 1-D bulk async copies (TMA engine) -- WarpStage in bgsa_common.cuh.  Warps take tiles of 32
-// subjects from a global counter (no tail imbalance, no block-level barrier after start-up).
-// HBM traffic per subject: slen/4 bytes in, 2 bytes out.
+// Launch geometry: grid = persistent CTAs (SMs x occupancy), THREADS threads.  Shared memory holds the
+// Peq (5 rows) of the query the CTA is working on and, per warp, a 2-stage buffer of subject tiles
+// filled by 1-D bulk async copies (TMA engine) -- WarpStage in bgsa_common.cuh.  Warps take (tile,
+// pass) work units from the query's counter (first unit static, then dynamic, claimed one ahead);
+// with several queries the CTAs are dealt over them round-robin and move on when a query runs dry.
+// HBM traffic per subject and query: slen/4 bytes in, 2 bytes out.
 #pragma once
 
 #include <type_traits>
