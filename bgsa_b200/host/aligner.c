@@ -190,6 +190,26 @@ int main(int argc, char **argv) {
     if (got < (size_t)(next_rows * stride)) rows_buf[0][got] = '\n';   /* file without final newline (file.c:64-72) */
     read_total_time += now_s() - t0;
 
+    /* Two (read bucket x ref bucket) items are in flight per device (slot = item & 1, the reference's a/b ping-pong,
+     * thread.c:35-170): item k+1 is queued before item k is waited for, so the GPUs never drain between buckets; results
+     * are written in item order. */
+    int64_t item = 0, item_nq[2] = {0, 0}, item_rows[2] = {0, 0};
+    int pending[2] = {0, 0};                 /* slot holds a submitted item whose results are not written yet */
+#define FINISH_ITEM(k)                                                                                         \
+    do {                                                                                                       \
+        const int s_ = (int)((k) & 1);                                                                         \
+        if (!pending[s_]) break;                                                                               \
+        pending[s_] = 0;                                                                                       \
+        double c0_ = now_s();                                                                                  \
+        for (int g = 0; g < ngpu; g++)                                                                         \
+            if (bgsa_align_batch_wait(g, s_) != BGSA_OK) die("Error - %s", bgsa_last_error());                 \
+        cal_total_time += now_s() - c0_;                                                                       \
+        double w0_ = now_s();                 /* output_task_cpu, thread.c:149-158 */                           \
+        fwrite(res_buf[s_], (size_t)esize, (size_t)item_nq[s_] * (size_t)item_rows[s_], fp_result);            \
+        fflush(fp_result);                                                                                     \
+        write_total_time += now_s() - w0_;                                                                     \
+    } while (0)
+
     for (int rb = 0; rb < read_bucket_num; rb++) {
         const int cur = rb & 1;
         const int64_t rows = next_rows;
@@ -211,37 +231,40 @@ int main(int argc, char **argv) {
             fwrite(&extra, sizeof(int), 1, fp_info);
             fflush(fp_info);
         }
-        for (int fb = 0; fb < ref_bucket_num; fb++) {
+        for (int fb = 0; fb < ref_bucket_num; fb++, item++) {
             const int ref_start = fb * ref_bucket_count;
             const int ref_end = (fb == ref_bucket_num - 1) ? (int)ref_count : (fb + 1) * ref_bucket_count;
             const int nq = ref_end - ref_start;
-            char *res = (char *)res_buf[fb & 1];
+            const int slot = (int)(item & 1);
+            FINISH_ITEM(item);                               /* item - 2: the slot and its result buffer must be free */
+            char *res = (char *)res_buf[slot];
+            item_nq[slot] = nq; item_rows[slot] = rows; pending[slot] = 1;
             double c0 = now_s();
             for (int g = 0; g < ngpu; g++) {   /* device-major result blocks (cal_mic.c:470-471) */
                 int rc = bgsa_align_batch_submit(&prm, ref + (int64_t)ref_start * (ref_len + 1), nq, ref_len, &seq, dev_first[g],
                                                  dev_count[g], res + (size_t)esize * (size_t)dev_first[g] * (size_t)nq,
-                                                 dev_count[g], g, 0);
+                                                 dev_count[g], g, slot);
                 if (rc != BGSA_OK) die("Error - %s", bgsa_last_error());
             }
-            /* overlap: while the GPUs work on this bucket, read the next one (input_task_cpu, thread.c:35-123) */
+            cal_total_time += now_s() - c0;
+            /* overlap: while the GPUs work on this bucket, read the next one (input_task_cpu, thread.c:35-123).  The
+             * other row buffer may still be read by the previous bucket's last item: finish that one first. */
             if (fb == 0 && rb + 1 < read_bucket_num) {
+                FINISH_ITEM(item + 1);                       /* item - 1 */
                 double r0 = now_s();
                 next_rows = total_rows - (rows_done + rows) < rows_per_bucket ? total_rows - (rows_done + rows) : rows_per_bucket;
                 got = fread(rows_buf[cur ^ 1], 1, (size_t)(next_rows * stride), fp_read);
                 if (got < (size_t)(next_rows * stride)) rows_buf[cur ^ 1][got] = '\n';
                 read_total_time += now_s() - r0;
             }
-            for (int g = 0; g < ngpu; g++)
-                if (bgsa_align_batch_wait(g, 0) != BGSA_OK) die("Error - %s", bgsa_last_error());
-            cal_total_time += now_s() - c0;
-            double w0 = now_s();                 /* output_task_cpu, thread.c:149-158 */
-            fwrite(res, (size_t)esize, (size_t)nq * (size_t)rows, fp_result);
-            fflush(fp_result);
-            write_total_time += now_s() - w0;
         }
         rows_done += rows;
         total_subjects += rows;
     }
+    /* drain: the (up to two) items still in flight, in order */
+    FINISH_ITEM(item);          /* item - 2 */
+    FINISH_ITEM(item + 1);      /* item - 1 */
+#undef FINISH_ITEM
     fclose(fp_ref); fclose(fp_read); fclose(fp_result); fclose(fp_info);
     double free_time = now_s();
     for (int b = 0; b < 2; b++) { bgsa_free_host(rows_buf[b]); bgsa_free_host(res_buf[b]); }
