@@ -160,7 +160,10 @@ int main(int argc, char **argv) {
     if (read_total_size == 0 || read_len == 0) die("Error - empty database file: %s", file_database);
     const int64_t stride = read_len + 1;
     const int64_t total_rows = (read_total_size + 1) / stride;       /* last newline optional (cal_cpu.c:241) */
-    int64_t rows_per_bucket = READ_BUCKET_SIZE / stride;
+    int64_t bucket_bytes = READ_BUCKET_SIZE;
+    if (getenv("BGSA_READ_BUCKET_SIZE")) bucket_bytes = atoll(getenv("BGSA_READ_BUCKET_SIZE"));   /* test knob: many small buckets */
+    int64_t rows_per_bucket = bucket_bytes / stride;
+    if (rows_per_bucket < 1) rows_per_bucket = 1;
     if (rows_per_bucket > total_rows) rows_per_bucket = total_rows;
     const int read_bucket_num = (int)((total_rows + rows_per_bucket - 1) / rows_per_bucket);
     if (bgsa_supported(&prm, ref_len, read_len) != BGSA_OK) die("Error - %s", bgsa_last_error());

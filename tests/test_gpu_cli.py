@@ -120,6 +120,29 @@ def test_aligner_multi_bucket_multi_query_vs_reference_aligner(tmp_path):
     assert (txt[:, idx] == R.oracle_batch(R.ALGO_MYERS_GLOBAL, q3, np.ascontiguousarray(s[idx]))).all()
 
 
+def test_aligner_many_items_in_flight_order(tmp_path):
+    """5 read buckets x 3 ref buckets (230 queries) = 15 pipelined items, two in flight: the payload must still be
+    read bucket -> ref bucket -> [query][subject] (cal_cpu.c:363-401), which convert -r undoes."""
+    convert = ROOT / "bgsa_b200" / "convert"
+    rng = np.random.default_rng(9)
+    q = R.random_rows(rng, 230, 60, with_n=0.01)
+    s = np.concatenate([R.mutate_rows(rng, q[7, :60], 2000, 12), R.random_rows(rng, 2611, 60, with_n=0.01)])
+    R.write_rows(tmp_path / "q.txt", q); R.write_rows(tmp_path / "s.txt", s)
+    env = dict(os.environ, BGSA_READ_BUCKET_SIZE=str(61 * 1000))          # 1000 rows per read bucket
+    for algo, oalgo, b in (("bitpal", R.ALGO_BITPAL_PACKED, "2"), ("myers", R.ALGO_MYERS_GLOBAL, "2")):
+        res = subprocess.run([str(ALIGNER), "-a", algo, "-q", "q.txt", "-d", "s.txt", "-f", "many.bin"], cwd=tmp_path, env=env,
+                             stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+        assert res.returncode == 0, res.stdout
+        nblocks, ndev, nq = struct.unpack("<iiq", (tmp_path / "many.bin.info").read_bytes()[:16])
+        assert (nblocks, ndev, nq) == (5, 1, 230)
+        run([convert, "-r", "many.bin", "-o", "many.txt", "-b", b], tmp_path)
+        txt = np.loadtxt(tmp_path / "many.txt", dtype=np.int64).reshape(230, -1)
+        assert (txt == R.oracle_batch(oalgo, q, s)).all(), algo
+        if (REF / "convert_int16").exists():
+            run([REF / "convert_int16", "-r", "many.bin", "-o", "many_ref.txt"], tmp_path)
+            assert md5(tmp_path / "many.txt") == md5(tmp_path / "many_ref.txt")
+
+
 def test_aligner_two_gpus_device_major_file(tmp_path):
     import torch
     if torch.cuda.device_count() < 2:
