@@ -22,7 +22,7 @@ import numpy as np
 __all__ = [
     "MYERS_GLOBAL", "MYERS_SEMIGLOBAL", "BANDED_MYERS", "BITPAL_PACKED", "BITPAL_NONPACKED", "BITPAL_PACKED_SEMIGLOBAL",
     "BgsaError", "Params", "SeqT", "load", "lib_path", "align_batch", "result_dtype", "to_codes",
-    "packed_bytes", "pack_subjects_device", "align_device", "int_peak", "bind_thread_to_device", "launch_count", "kernel_name", "supported",
+    "packed_bytes", "pack_subjects_device", "align_device", "align_rows_device", "int_peak", "bind_thread_to_device", "launch_count", "kernel_name", "supported",
 ]
 
 MYERS_GLOBAL, MYERS_SEMIGLOBAL, BANDED_MYERS, BITPAL_PACKED, BITPAL_NONPACKED, BITPAL_PACKED_SEMIGLOBAL = range(6)
@@ -90,6 +90,7 @@ def load():
         "bgsa_packed_bytes": (i64, [i32, i64]),
         "bgsa_pack_subjects_device": (i32, [PP, vp, i32, i64, vp, i32, vp]),
         "bgsa_align_device": (i32, [PP, vp, i32, i32, vp, i32, i64, vp, i64, i32, vp]),
+        "bgsa_align_rows_device": (i32, [PP, vp, i32, i32, vp, i32, i64, vp, i64, i32, vp]),
         "bgsa_launch_count": (i64, []),
         "bgsa_kernel_name": (i32, [PP, i32, i32, C.c_char_p, i32]),
         "bgsa_int_peak": (i32, [i32, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
@@ -106,7 +107,7 @@ EXPORTED_SYMBOLS = [
     "bgsa_version", "bgsa_last_error", "bgsa_device_count", "bgsa_init_devices", "bgsa_params_default", "bgsa_result_size", "bgsa_supported",
     "bgsa_align_batch", "bgsa_align_batch_submit", "bgsa_align_batch_wait", "bgsa_malloc_host", "bgsa_free_host",
     "bgsa_host_register", "bgsa_host_unregister", "bgsa_bind_thread_to_device",
-    "bgsa_packed_bytes", "bgsa_pack_subjects_device", "bgsa_align_device", "bgsa_launch_count", "bgsa_kernel_name",
+    "bgsa_packed_bytes", "bgsa_pack_subjects_device", "bgsa_align_device", "bgsa_align_rows_device", "bgsa_launch_count", "bgsa_kernel_name",
     "bgsa_int_peak", "bgsa_align_peq_chunk",
 ]
 
@@ -191,6 +192,14 @@ def bind_thread_to_device(device: int = 0) -> int:
     node = C.c_int(-1)
     _check(load().bgsa_bind_thread_to_device(device, C.byref(node)))
     return node.value
+
+
+def align_rows_device(params: Params, queries: np.ndarray, d_rows_ptr: int, subject_len: int, count: int,
+                      d_results_ptr: int, result_stride: int, device: int = 0, stream: int = 0) -> None:
+    """Device-resident ASCII rows -> scores (pack + align, or the fused banded kernel)."""
+    qc = np.ascontiguousarray(to_codes(np.asarray(queries, dtype=np.uint8)))
+    _check(load().bgsa_align_rows_device(C.byref(params), qc.ctypes.data, qc.shape[0], qc.shape[1] - 1, d_rows_ptr,
+                                         subject_len, count, d_results_ptr, result_stride, device, stream))
 
 
 def int_peak(device: int = 0):

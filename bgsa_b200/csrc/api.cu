@@ -179,8 +179,9 @@ struct DeviceCtx {
     bool ready = false;
     int sm_count = 0;
     Job job[2];
-    QueryCache resident_qc;  // bgsa_align_device (caller's stream)
+    QueryCache resident_qc;  // bgsa_align_device / bgsa_align_rows_device (caller's stream)
     Buf resident_counters;
+    Buf resident_packed;     // bgsa_align_rows_device: packed form of the caller's rows (algorithms without a fused kernel)
 };
 constexpr int kMaxDevices = 64;
 DeviceCtx g_ctx[kMaxDevices];
@@ -246,7 +247,7 @@ int stage_queries(QueryCache &qc, const Plan &plan, const char *queries, int nq,
 
 int run_align(const Plan &plan, int sm_count, const void *d_tab, unsigned long long *d_counters, int nq, int qlen,
               const void *d_packed, int slen, int64_t count, void *d_results, int64_t result_stride, cudaStream_t stream,
-              long long *resident_subjects = nullptr) {
+              long long *resident_subjects = nullptr, const void *d_ascii_rows = nullptr) {
     if ((count == 0 || nq == 0) && !resident_subjects) return BGSA_OK;
     LaunchArgs a;
     a.dry_run = resident_subjects != nullptr;
@@ -267,7 +268,7 @@ int run_align(const Plan &plan, int sm_count, const void *d_tab, unsigned long l
         case BGSA_BITPAL_PACKED:    e = launch_bitpal_packed(plan.scheme, plan.kl.K, plan.kl.L, a); break;
         case BGSA_BITPAL_NONPACKED: e = launch_bitpal_nonpacked(plan.scheme, plan.kl.K, plan.kl.L, a); break;
         case BGSA_BITPAL_PACKED_SEMIGLOBAL: e = launch_bitpal_semiglobal(plan.scheme, plan.kl.K, plan.kl.L, a); break;
-        case BGSA_BANDED_MYERS:     e = launch_banded(a, d_tab, plan.e); break;
+        case BGSA_BANDED_MYERS:     e = d_ascii_rows ? launch_banded_fused(a, d_ascii_rows, d_tab, plan.e) : launch_banded(a, d_tab, plan.e); break;
         default: return fail(BGSA_ERR_ARG, "unknown algorithm %d", plan.algo);
     }
     if (e != cudaSuccess) return fail(BGSA_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
@@ -441,6 +442,34 @@ int bgsa_align_device(const bgsa_params_t *p, const char *h_queries, int n_queri
     if ((rc = ctx->resident_counters.ensure(sizeof(unsigned long long) * (size_t)n_queries))) return rc;
     return run_align(plan, ctx->sm_count, d_tab, static_cast<unsigned long long *>(ctx->resident_counters.p), n_queries,
                      query_len, d_packed, subject_len, count, d_results, result_stride, st);
+}
+
+int bgsa_align_rows_device(const bgsa_params_t *p, const char *h_queries, int n_queries, int query_len, const void *d_rows,
+                           int subject_len, int64_t count, void *d_results, int64_t result_stride, int device, void *stream) {
+    Plan plan;
+    int rc = make_plan(p, query_len, subject_len, &plan);
+    if (rc) return rc;
+    if (!h_queries || n_queries < 0 || count < 0 || (count > 0 && (!d_rows || !d_results)) || result_stride < count)
+        return fail(BGSA_ERR_ARG, "bgsa_align_rows_device: bad argument");
+    DeviceCtx *ctx;
+    rc = get_ctx(device, &ctx);
+    if (rc) return rc;
+    if (count == 0 || n_queries == 0) return BGSA_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const void *d_tab;
+    rc = stage_queries(ctx->resident_qc, plan, h_queries, n_queries, query_len, subject_len, st, &d_tab);
+    if (rc) return rc;
+    if ((rc = ctx->resident_counters.ensure(sizeof(unsigned long long) * (size_t)n_queries))) return rc;
+    unsigned long long *d_counters = static_cast<unsigned long long *>(ctx->resident_counters.p);
+    if (plan.algo == BGSA_BANDED_MYERS && banded_fused_fits(subject_len))     // ASCII in, scores out, one kernel
+        return run_align(plan, ctx->sm_count, d_tab, d_counters, n_queries, query_len, nullptr, subject_len, count, d_results,
+                         result_stride, st, nullptr, d_rows);
+    if ((rc = ctx->resident_packed.ensure((size_t)packed_bytes(subject_len, count)))) return rc;
+    cudaError_t e = launch_pack(plan.layout, d_rows, subject_len, count, ctx->resident_packed.p, ctx->sm_count, st);
+    if (e != cudaSuccess) return fail(BGSA_ERR_CUDA, "pack kernel launch failed: %s", cudaGetErrorString(e));
+    g_launches.fetch_add(1);
+    return run_align(plan, ctx->sm_count, d_tab, d_counters, n_queries, query_len, ctx->resident_packed.p, subject_len, count,
+                     d_results, result_stride, st);
 }
 
 int bgsa_align_batch_submit(const bgsa_params_t *p, const char *queries, int n_queries, int query_len,

@@ -25,6 +25,7 @@
 #pragma once
 
 #include "bgsa_common.cuh"
+#include "pack.cuh"
 
 namespace bgsa {
 
@@ -47,13 +48,27 @@ template <> struct BandWord<true> { using type = uint64_t; };
 //  takes 61 and the occupancy drops to 8)
 // MULTI = false (one query): the row-mask table and the result row are kernel-wide constants (uniform-register
 // addressing); MULTI = true: they change with the work unit's query.
-template <bool WIDE, bool MULTI, int THREADS>
-__global__ void __launch_bounds__(THREADS, WIDE ? 8 : 10)
-banded_kernel(PackedSubjects ps, const BandedRow *__restrict__ g_rows, int n_queries, int qlen, int e,
-              int8_t *__restrict__ results, long long result_stride, unsigned long long *__restrict__ counters) {
+// FUSED = true: the subjects come as ASCII rows (`ascii`, stride slen+1; ps only carries the geometry): the warp
+// encodes its tile into a shared-memory strip first (step 1 of the streaming pack, pack.cuh) and the lanes cut their
+// bit-plane words out of the strip instead of loading packed tiles -- no packed round trip through HBM, and the
+// memory-bound encode of one warp overlaps the ALU-bound band rows of the others.
+template <bool WIDE, bool MULTI, bool FUSED, int THREADS>
+__global__ void __launch_bounds__(THREADS, FUSED ? (WIDE ? 7 : 9) : (WIDE ? 8 : 10))
+banded_kernel(PackedSubjects ps, const uint8_t *__restrict__ ascii, const BandedRow *__restrict__ g_rows, int n_queries, int qlen,
+              int e, int8_t *__restrict__ results, long long result_stride, unsigned long long *__restrict__ counters) {
     using T = typename BandWord<WIDE>::type;
+    extern __shared__ __align__(16) uint32_t s_strips[];       // FUSED: one strip per warp
     const int lane = threadIdx.x & 31;
     const int ku = ps.ku;
+    const int stride = ps.slen + 1;
+    uint32_t *s_c = s_strips + (threadIdx.x >> 5) * (FUSED ? pack_warp_words(stride, 1) : 0);
+    uint16_t *s_n = reinterpret_cast<uint16_t *>(s_c + (FUSED ? pack_code_words(stride, 1) : 0));
+    const int off = FUSED ? (int)(reinterpret_cast<uintptr_t>(ascii) & 15) : 0;
+    const int inc = 512 % stride;
+    int m0 = (16 * lane - off) % stride;
+    if (m0 < 0) m0 += stride;
+    const int base_pos = off + lane * stride;                 // strip position of this lane's own row
+    const int wi0 = base_pos >> 4, sub = base_pos & 15;
     const int sh = e + 1;                                     // plane index u = i + e + 1
     const int C = qlen <= 64 ? qlen : max(64, qlen - e);      // rows done at the last checkpoint
     const int max_err = 2 * e + 1;                            // threshold + h_threshold + 1 (:114)
@@ -66,7 +81,19 @@ banded_kernel(PackedSubjects ps, const BandedRow *__restrict__ g_rows, int n_que
         const long long tile = work - (long long)q * ps.ntiles;
         const BandedRow *rows = MULTI ? g_rows + (size_t)q * qlen : g_rows;
         int8_t *out = MULTI ? results + (long long)q * result_stride : results;
-        const bool with_n = ps.tile_has_n[tile] != 0;
+        bool with_n;
+        if (FUSED) {
+            const long long first = tile * kTileSubjects;
+            const int live_rows = (int)min((long long)kTileSubjects, ps.count - first);
+            const int npieces = (off + live_rows * stride + 15) >> 4;
+            __syncwarp();                                      // the previous tile's strip is no longer read
+            const uint32_t any_n = pack_run_to_strip<LAYOUT_PLANES, false>(reinterpret_cast<const uint4 *>(ascii + first * stride - off), npieces,
+                                                                    ps.slen, stride, inc, m0, lane, s_c, s_n);
+            with_n = __ballot_sync(0xffffffffu, any_n != 0u) != 0u;
+            __syncwarp();
+        } else {
+            with_n = ps.tile_has_n[tile] != 0;
+        }
         const uint4 *src = ps.codes + tile * ku * 32 + lane;
         const uint32_t *nsrc = ps.nmask + tile * ps.kn * 32 + lane;
         T VP = 0, VN = 0;
@@ -78,7 +105,13 @@ banded_kernel(PackedSubjects ps, const BandedRow *__restrict__ g_rows, int n_que
         uint4 unit = make_uint4(0u, 0u, 0u, 0u);
         auto plane_word = [&](int k, uint32_t &lo, uint32_t &hi, uint32_t &nn) {
             lo = hi = nn = 0u;
-            if (k >= 0 && k < 2 * ku) {
+            if (FUSED) {
+                // (dead lanes of the last tile read stale strip words: harmless, their result is not stored)
+                if (k >= 0 && k < 2 * ku) {
+                    strip_plane_word(s_c, wi0, sub, k, ps.slen, lo, hi);
+                    if (with_n && k < ps.kn) nn = strip_n_word(s_n, wi0, sub, k, ps.slen);
+                }
+            } else if (k >= 0 && k < 2 * ku) {
                 if ((k & 1) == 0) unit = __ldg(src + (long long)(k >> 1) * 32);
                 lo = (k & 1) ? unit.z : unit.x;
                 hi = (k & 1) ? unit.w : unit.y;

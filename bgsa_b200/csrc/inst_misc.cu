@@ -42,34 +42,42 @@ cudaError_t launch_bitpal_nonpacked(int scheme, int K, int L, const LaunchArgs &
 }
 
 // ---- banded ------------------------------------------------------------------------------------
-template <bool WIDE>
-static cudaError_t launch_banded_t(const LaunchArgs &a, const void *d_rows_table, int e) {
+template <bool WIDE, bool FUSED>
+static cudaError_t launch_banded_t(const LaunchArgs &a, const uint8_t *ascii, const void *d_rows_table, int e) {
     constexpr int THREADS = 128;
     const bool multi = a.n_queries > 1;
-    auto kern = multi ? banded_kernel<WIDE, true, THREADS> : banded_kernel<WIDE, false, THREADS>;
-    static int occ = 0;
-    if (occ == 0) {
-        cudaError_t err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, 0);
-        if (err != cudaSuccess) return err;
-        if (occ < 1) occ = 1;
-    }
+    auto kern = multi ? banded_kernel<WIDE, true, FUSED, THREADS> : banded_kernel<WIDE, false, FUSED, THREADS>;
+    const size_t smem = FUSED ? sizeof(uint32_t) * (size_t)pack_warp_words(a.ps.slen + 1, 1) * (THREADS / 32) : 0;
+    if (smem > 48 * 1024) return cudaErrorInvalidValue;        // callers route long rows to pack + align
+    int occ = 0;                                               // (cheap; depends on smem for FUSED)
+    cudaError_t err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, smem);
+    if (err != cudaSuccess) return err;
+    if (occ < 1) occ = 1;
     if (a.dry_run) {
         if (a.resident_subjects) *a.resident_subjects = (long long)a.sm_count * occ * (THREADS / 32) * 32;
         return cudaSuccess;
     }
-    cudaError_t err = cudaMemsetAsync(a.d_counters, 0, sizeof(unsigned long long) * a.n_queries, a.stream);
+    err = cudaMemsetAsync(a.d_counters, 0, sizeof(unsigned long long) * a.n_queries, a.stream);
     if (err != cudaSuccess) return err;
     const int nq = a.n_queries > 0 ? a.n_queries : 1;
     long long want = (a.ps.ntiles * nq + 3) / 4;
     const long long resident = (long long)a.sm_count * occ;
     if (want > resident) want = resident;
     if (want < 1) want = 1;
-    kern<<<(unsigned)want, THREADS, 0, a.stream>>>(a.ps, static_cast<const BandedRow *>(d_rows_table), nq, a.qlen, e,
-                                                   static_cast<int8_t *>(a.d_results), a.result_stride, a.d_counters);
+    kern<<<(unsigned)want, THREADS, smem, a.stream>>>(a.ps, ascii, static_cast<const BandedRow *>(d_rows_table), nq, a.qlen, e,
+                                                      static_cast<int8_t *>(a.d_results), a.result_stride, a.d_counters);
     return cudaGetLastError();
 }
 cudaError_t launch_banded(const LaunchArgs &a, const void *d_rows_table, int e) {
-    return (2 * e + 2 <= 32) ? launch_banded_t<false>(a, d_rows_table, e) : launch_banded_t<true>(a, d_rows_table, e);
+    return (2 * e + 2 <= 32) ? launch_banded_t<false, false>(a, nullptr, d_rows_table, e)
+                             : launch_banded_t<true, false>(a, nullptr, d_rows_table, e);
+}
+// ASCII rows in, scores out, one kernel (rows short enough for a warp's strip in 48 KB of shared memory: ~950 bases)
+bool banded_fused_fits(int slen) { return sizeof(uint32_t) * (size_t)pack_warp_words(slen + 1, 1) * 4 <= 48 * 1024 && slen + 1 >= 16; }
+cudaError_t launch_banded_fused(const LaunchArgs &a, const void *d_ascii_rows, const void *d_rows_table, int e) {
+    const uint8_t *rows = static_cast<const uint8_t *>(d_ascii_rows);
+    return (2 * e + 2 <= 32) ? launch_banded_t<false, true>(a, rows, d_rows_table, e)
+                             : launch_banded_t<true, true>(a, rows, d_rows_table, e);
 }
 
 // ---- pack ----------------------------------------------------------------------------------------

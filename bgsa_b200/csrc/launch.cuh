@@ -56,6 +56,8 @@ cudaError_t launch_bitpal_packed(int scheme, int K, int L, const LaunchArgs &a);
 cudaError_t launch_bitpal_semiglobal(int scheme, int K, int L, const LaunchArgs &a);
 cudaError_t launch_bitpal_nonpacked(int scheme, int K, int L, const LaunchArgs &a);
 cudaError_t launch_banded(const LaunchArgs &a, const void *d_rows_table, int e);
+bool banded_fused_fits(int slen);
+cudaError_t launch_banded_fused(const LaunchArgs &a, const void *d_ascii_rows, const void *d_rows_table, int e);
 cudaError_t launch_pack(int layout, const void *d_rows, int slen, long long count, void *d_packed, int sm_count,
                         cudaStream_t stream);
 cudaError_t launch_unpeq(int layout, int wordbytes, const void *d_peq, int word_num, int usable, int head, int slen,

@@ -200,6 +200,81 @@ __device__ __forceinline__ uint32_t encode_piece(const uint4 v, int e, uint32_t 
     return accbad;
 }
 
+// Step 1 of the streaming pack for one warp (also used by the fused banded kernel): encodes the `npieces` 16-byte
+// pieces at `src` into the warp's strip (s_c: one word per piece, s_n: its N bits) and returns the OR of the N bits
+// this lane produced.  m0 = position of the lane's first piece inside its row, inc = 512 % stride.
+template <int LAYOUT, bool PREFETCH = true>
+__device__ __forceinline__ uint32_t pack_run_to_strip(const uint4 *__restrict__ src, int npieces, int slen, int stride, int inc,
+                                                      int m0, int lane, uint32_t *s_c, uint16_t *s_n) {
+    // stream order.  Whole groups of kPackUnroll x 32 pieces first (no bounds checks, loads in
+    // flight before the first is used), then the remainder one piece per lane and trip.
+    uint32_t any_n = 0u;
+    int m = m0;
+    const int full = npieces - npieces % (32 * kPackUnroll);
+    int p0 = lane;
+    // current / next group (software prefetch; not worth its 16 registers when a run is a single short tile)
+    uint4 v[kPackUnroll], nv[PREFETCH ? kPackUnroll : 1];
+    if (PREFETCH && p0 < full) {
+#pragma unroll
+        for (int k = 0; k < kPackUnroll; k++) v[k] = __ldg(src + p0 + 32 * k);
+    }
+    for (; p0 < full; p0 += 32 * kPackUnroll) {
+        if (PREFETCH) {
+            if (p0 + 32 * kPackUnroll < full) {                  // warp-uniform
+#pragma unroll
+                for (int k = 0; k < kPackUnroll; k++) nv[k] = __ldg(src + p0 + 32 * kPackUnroll + 32 * k);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < kPackUnroll; k++) v[k] = __ldg(src + p0 + 32 * k);
+        }
+        const int ph = pack_phys(p0);                           // pack_phys(p0 + 32k) = ph + 33k
+        uint32_t redo = 0u;                                     // bit k: piece k needs the exact path
+#pragma unroll
+        for (int k = 0; k < kPackUnroll; k++) {
+            uint32_t cw;
+            const uint32_t bad = encode_piece<LAYOUT>(v[k], slen - m, cw);
+            m += inc;
+            if (m >= stride) m -= stride;
+            s_c[ph + 33 * k] = cw;
+            s_n[p0 + 32 * k] = (uint16_t)0;
+            redo |= (bad != 0u ? 1u : 0u) << k;
+        }
+        while (redo) {                                          // rare: 'N', lower case, ...
+            const int k = __ffs(redo) - 1;
+            redo &= redo - 1u;
+            const int p = p0 + 32 * k;
+            const uint2 r = encode_piece_exact<LAYOUT>(__ldg(src + p));
+            s_c[pack_phys(p)] = r.x;
+            s_n[p] = (uint16_t)r.y;
+            any_n |= r.y;
+        }
+        if (PREFETCH) {
+#pragma unroll
+            for (int k = 0; k < kPackUnroll; k++) v[k] = nv[k];
+        }
+    }
+    uint32_t redo_tail = 0u;                                    // bit i: tail piece p0 + 32 i needs the exact path
+    for (int p = p0, i = 0; p < npieces; p += 32, i++) {
+        uint32_t cw;
+        const uint32_t bad = encode_piece<LAYOUT>(__ldg(src + p), slen - m, cw);
+        m += inc;
+        if (m >= stride) m -= stride;
+        s_c[pack_phys(p)] = cw;
+        s_n[p] = (uint16_t)0;
+        redo_tail |= (bad != 0u ? 1u : 0u) << i;
+    }
+    while (redo_tail) {
+        const int p = p0 + 32 * (__ffs(redo_tail) - 1);
+        redo_tail &= redo_tail - 1u;
+        const uint2 r = encode_piece_exact<LAYOUT>(__ldg(src + p));
+        s_c[pack_phys(p)] = r.x;
+        s_n[p] = (uint16_t)r.y;
+        any_n |= r.y;
+    }
+    return any_n;
+}
+
 template <int LAYOUT>
 __global__ void __launch_bounds__(128)
 pack_stream_kernel(const uint8_t *__restrict__ rows, int slen, long long count, uint4 *__restrict__ codes,
@@ -223,64 +298,8 @@ pack_stream_kernel(const uint8_t *__restrict__ rows, int slen, long long count, 
         const int pass_rows = (int)min((long long)kTileSubjects * G, count - first);
         const uint4 *src = reinterpret_cast<const uint4 *>(rows + first * stride - off);
         const int npieces = (off + pass_rows * stride + 15) >> 4;
-        // ---- step 1: stream order.  Whole groups of kPackUnroll x 32 pieces first (no bounds checks, loads in
-        // flight before the first is used), then the remainder one piece per lane and trip.
-        uint32_t any_n = 0u;
-        int m = m0;
-        const int full = npieces - npieces % (32 * kPackUnroll);
-        int p0 = lane;
-        uint4 v[kPackUnroll], nv[kPackUnroll];                      // current / next group (software prefetch)
-        if (p0 < full) {
-#pragma unroll
-            for (int k = 0; k < kPackUnroll; k++) v[k] = __ldg(src + p0 + 32 * k);
-        }
-        for (; p0 < full; p0 += 32 * kPackUnroll) {
-            if (p0 + 32 * kPackUnroll < full) {                      // warp-uniform
-#pragma unroll
-                for (int k = 0; k < kPackUnroll; k++) nv[k] = __ldg(src + p0 + 32 * kPackUnroll + 32 * k);
-            }
-            const int ph = pack_phys(p0);                           // pack_phys(p0 + 32k) = ph + 33k
-            uint32_t redo = 0u;                                     // bit k: piece k needs the exact path
-#pragma unroll
-            for (int k = 0; k < kPackUnroll; k++) {
-                uint32_t cw;
-                const uint32_t bad = encode_piece<LAYOUT>(v[k], slen - m, cw);
-                m += inc;
-                if (m >= stride) m -= stride;
-                s_c[ph + 33 * k] = cw;
-                s_n[p0 + 32 * k] = (uint16_t)0;
-                redo |= (bad != 0u ? 1u : 0u) << k;
-            }
-            while (redo) {                                          // rare: 'N', lower case, ...
-                const int k = __ffs(redo) - 1;
-                redo &= redo - 1u;
-                const int p = p0 + 32 * k;
-                const uint2 r = encode_piece_exact<LAYOUT>(__ldg(src + p));
-                s_c[pack_phys(p)] = r.x;
-                s_n[p] = (uint16_t)r.y;
-                any_n |= r.y;
-            }
-#pragma unroll
-            for (int k = 0; k < kPackUnroll; k++) v[k] = nv[k];
-        }
-        uint32_t redo_tail = 0u;                                    // bit i: tail piece p0 + 32 i needs the exact path
-        for (int p = p0, i = 0; p < npieces; p += 32, i++) {
-            uint32_t cw;
-            const uint32_t bad = encode_piece<LAYOUT>(__ldg(src + p), slen - m, cw);
-            m += inc;
-            if (m >= stride) m -= stride;
-            s_c[pack_phys(p)] = cw;
-            s_n[p] = (uint16_t)0;
-            redo_tail |= (bad != 0u ? 1u : 0u) << i;
-        }
-        while (redo_tail) {
-            const int p = p0 + 32 * (__ffs(redo_tail) - 1);
-            redo_tail &= redo_tail - 1u;
-            const uint2 r = encode_piece_exact<LAYOUT>(__ldg(src + p));
-            s_c[pack_phys(p)] = r.x;
-            s_n[p] = (uint16_t)r.y;
-            any_n |= r.y;
-        }
+        // ---- step 1: stream order
+        const uint32_t any_n = pack_run_to_strip<LAYOUT>(src, npieces, slen, stride, inc, m0, lane, s_c, s_n);
         const bool pass_n = __ballot_sync(0xffffffffu, any_n != 0u) != 0u;
         __syncwarp();
         // ---- step 2: subject order, tile by tile
@@ -344,6 +363,24 @@ pack_stream_kernel(const uint8_t *__restrict__ rows, int slen, long long count, 
         }
         __syncwarp();      // the strip is rewritten by the next pass
     }
+}
+
+// Readers of a PLANES strip (word per 16 bases = low plane | high plane << 16) for a row that starts at strip position
+// wi0*16 + sub: the low / high bit-plane word (32 bases) number k of the row, bases beyond slen cleared.
+__device__ __forceinline__ void strip_plane_word(const uint32_t *s_c, int wi0, int sub, int k, int slen, uint32_t &lo, uint32_t &hi) {
+    const uint32_t t0 = s_c[pack_phys(wi0 + 2 * k)], t1 = s_c[pack_phys(wi0 + 2 * k + 1)], t2 = s_c[pack_phys(wi0 + 2 * k + 2)];
+    lo = __funnelshift_r(prmt(t0, t1, 0x5410u), t2 & 0xffffu, sub);
+    hi = __funnelshift_r(prmt(t0, t1, 0x7632u), t2 >> 16, sub);
+    const int nb = slen - 32 * k;
+    if (nb < 32) { const uint32_t keep = nb <= 0 ? 0u : ((1u << nb) - 1u); lo &= keep; hi &= keep; }
+}
+__device__ __forceinline__ uint32_t strip_n_word(const uint16_t *s_n, int wi0, int sub, int k, int slen) {
+    const int q = wi0 + 2 * k;
+    const uint32_t a = (uint32_t)s_n[q] | ((uint32_t)s_n[q + 1] << 16), b = s_n[q + 2];
+    uint32_t nm = __funnelshift_r(a, b, sub);
+    const int nb = slen - 32 * k;
+    if (nb < 32) nm &= nb <= 0 ? 0u : ((1u << nb) - 1u);
+    return nm;
 }
 
 // Peq -> tiles, for the per-chunk drop-in entry points (include/align_core.h): recovers the subject

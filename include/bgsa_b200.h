@@ -131,6 +131,12 @@ int bgsa_pack_subjects_device(const bgsa_params_t *p, const void *d_rows, int su
 int bgsa_align_device(const bgsa_params_t *p, const char *h_queries, int n_queries, int query_len,
                       const void *d_packed, int subject_len, int64_t count,
                       void *d_results, int64_t result_stride, int device, void *stream);
+/* d_rows: device pointer to ASCII rows (stride subject_len+1), as bgsa_pack_subjects_device takes them; scores to
+ * d_results.  Packs into a library-owned buffer and aligns, or -- banded Myers on rows up to ~950 bases -- runs ONE
+ * kernel that encodes every tile into shared memory and verifies it in place (no packed round trip through HBM). */
+int bgsa_align_rows_device(const bgsa_params_t *p, const char *h_queries, int n_queries, int query_len,
+                           const void *d_rows, int subject_len, int64_t count,
+                           void *d_results, int64_t result_stride, int device, void *stream);
 /* Number of kernel launches issued by this library since load (bench.py "gpu_launches"). */
 int64_t bgsa_launch_count(void);
 /* Name of the kernel instance bgsa_align_device would use, e.g. "bitpal_packed<2,-3,-5,K=5,L=1>". */

@@ -430,3 +430,45 @@ def test_query_counts_beyond_the_grid(B, nq, ns):
     if nq == 300:    # a wavefront instance as well (L > 1)
         ql = R.random_rows(rng, 40, 700); sl = R.random_rows(rng, 50, 200)
         assert (B.align_batch(B.Params.default(B.BITPAL_PACKED), ql, sl) == R.oracle_batch(3, ql, sl)).all()
+
+
+@pytest.mark.parametrize("slen,n,e", [(100, 5000, 5), (100, 4099, 15), (64, 333, 3), (50, 97, 5), (250, 1000, 7), (333, 100, 31),
+                                      (640, 200, 20), (900, 70, 10), (1000, 60, 10), (33, 64, 1), (15, 40, 2)])
+def test_rows_device_entry_banded_fused(B, slen, n, e):
+    """bgsa_align_rows_device: ASCII rows resident in HBM -> scores.  For banded Myers this is the fused kernel (tile
+    encoded into shared memory, band run from there); rows with N / arbitrary bytes, several queries, a row buffer
+    that is not 16-byte aligned, counts off the tile grid.  (slen 1000: falls back to pack + align.)"""
+    import torch
+    rng = np.random.default_rng(slen * 13 + n)
+    q = R.random_rows(rng, 3, slen, with_n=0.004)
+    s = np.concatenate([R.mutate_rows(rng, q[0, :slen], n // 2, 2 * e + 2), R.indel_rows(rng, q[1, :slen], n // 4, e + 3),
+                        R.random_rows(rng, n - n // 2 - n // 4, slen, with_n=0.01)])
+    junk = rng.random(s[:, :slen].shape) < 0.002
+    s[:, :slen][junk] = rng.integers(0, 256, size=int(junk.sum()), dtype=np.uint8)
+    p = B.Params.default(B.BANDED_MYERS, threshold=e)
+    exp = R.oracle_batch(R.ALGO_BANDED, q, s, e=e)
+    inb = ((slen - 1) // 64 + 1) < ((slen - e + 63) // 64 + 1)
+    for shift in (0, 7):
+        buf = torch.zeros(s.size + 64, dtype=torch.uint8, device="cuda")
+        buf[shift:shift + s.size] = torch.from_numpy(s.reshape(-1)).cuda()
+        d_res = torch.full((3 * n,), 99, dtype=torch.int8, device="cuda")
+        before = B.launch_count()
+        B.align_rows_device(p, q, buf.data_ptr() + shift, slen, n, d_res.data_ptr(), n)
+        torch.cuda.synchronize()
+        got = d_res.cpu().numpy().reshape(3, n)
+        assert B.launch_count() - before == (1 if slen <= 900 else 2)        # fused: one kernel
+        assert (got == B.align_batch(p, q, s)).all()                         # the two-kernel path agrees
+        if inb:
+            assert (got == exp).all(), (slen, n, e, shift)
+
+
+def test_rows_device_entry_other_algorithms(B):
+    import torch
+    rng = np.random.default_rng(77)
+    q = R.random_rows(rng, 2, 150, with_n=0.01); s = R.random_rows(rng, 3001, 170, with_n=0.01)
+    d_rows = torch.from_numpy(s.reshape(-1)).cuda()
+    for algo, oalgo in ((B.MYERS_GLOBAL, 0), (B.MYERS_SEMIGLOBAL, 1), (B.BITPAL_PACKED, 3), (B.BITPAL_PACKED_SEMIGLOBAL, 5)):
+        d_res = torch.zeros(2 * 3001 * 2, dtype=torch.uint8, device="cuda")
+        B.align_rows_device(B.Params.default(algo), q, d_rows.data_ptr(), 170, 3001, d_res.data_ptr(), 3001)
+        torch.cuda.synchronize()
+        assert (d_res.cpu().numpy().view(np.int16).reshape(2, 3001) == R.oracle_batch(oalgo, q, s)).all(), algo

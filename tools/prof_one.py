@@ -17,8 +17,11 @@ d_rows = torch.from_numpy(s.reshape(-1)).cuda()
 d_packed = torch.empty(B.packed_bytes(sl, count), dtype=torch.uint8, device="cuda")
 d_res = torch.zeros(count * 2, dtype=torch.uint8, device="cuda")
 st = torch.cuda.current_stream().cuda_stream
-for _ in range(reps):
-    B.pack_subjects_device(p, d_rows.data_ptr(), sl, count, d_packed.data_ptr(), 0, st)
-    B.align_device(p, q, d_packed.data_ptr(), sl, count, d_res.data_ptr(), count, 0, st)
+for _ in range(reps):      # the same resident step as bench.py times
+    if algo == B.BANDED_MYERS:
+        B.align_rows_device(p, q, d_rows.data_ptr(), sl, count, d_res.data_ptr(), count, 0, st)
+    else:
+        B.pack_subjects_device(p, d_rows.data_ptr(), sl, count, d_packed.data_ptr(), 0, st)
+        B.align_device(p, q, d_packed.data_ptr(), sl, count, d_res.data_ptr(), count, 0, st)
 torch.cuda.synchronize()
 print("done", name, count)

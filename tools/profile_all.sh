@@ -9,7 +9,7 @@ mkdir -p "$OUT"
 BENCH="python bench.py --steps 2 --warmup 3 --no-cpu-baseline"
 $BENCH > "$OUT/bench_plain.log" 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file "$OUT/launches_bench_C2.csv" $BENCH > "$OUT/bench_under_ncu.log" 2>&1
-for spec in "C2 1000000 align_kernel" "C3 10000000 banded_kernel" "C4 1000000 align_kernel" "C5 32768 align_kernel" "myers150 1000000 align_kernel" "C3 10000000 pack_stream" "C2 1000000 pack_stream"; do
+for spec in "C2 1000000 align_kernel" "C3 10000000 banded_kernel" "C4 1000000 align_kernel" "C5 32768 align_kernel" "myers150 1000000 align_kernel" "C4 1000000 pack_stream" "C2 1000000 pack_stream"; do
     set -- $spec
     python tools/prof_one.py $1 $2 2 > "$OUT/plain_$1_$3.log" 2>&1 &&
     ncu --set full --clock-control none --import-source on -k regex:$3 -s 1 -c 1 -f -o "$OUT/full_$1_$3" python tools/prof_one.py $1 $2 2 > "$OUT/ncu_$1_$3.log" 2>&1
