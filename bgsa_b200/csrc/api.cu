@@ -519,6 +519,8 @@ int bgsa_align_batch_submit(const bgsa_params_t *p, const char *queries, int n_q
         job.trace.clear();
         CUDA_TRY(cudaEventRecord(job.t0, job.lane[0].stream));
     }
+    // banded Myers on short rows: one fused kernel per chunk (ASCII tile -> shared-memory strip -> band), no pack launch
+    const bool fused = plan.algo == BGSA_BANDED_MYERS && banded_fused_fits(slen);
     int li = 0;
     for (int64_t off = 0, step = first_chunk; off < count; off += step, step = chunk, li = (li + 1) % kLanesPerJob) {
         const int64_t n = count - off < step ? count - off : step;
@@ -529,20 +531,22 @@ int bgsa_align_batch_submit(const bgsa_params_t *p, const char *queries, int n_q
         };
         const size_t row_bytes = (size_t)n * (slen + 1);
         if ((rc = l.d_rows.ensure(row_bytes + 16))) return rc;
-        if ((rc = l.d_packed.ensure((size_t)packed_bytes(slen, n)))) return rc;
+        if (!fused && (rc = l.d_packed.ensure((size_t)packed_bytes(slen, n)))) return rc;
         if ((rc = l.d_results.ensure(esize * (size_t)n_queries * (size_t)n))) return rc;
         if ((rc = l.d_counters.ensure(sizeof(unsigned long long) * (size_t)n_queries))) return rc;
         // host -> device: the ASCII rows exactly as file.c:44-115 left them
         CUDA_TRY(cudaMemcpyAsync(l.d_rows.p, subjects->content + (size_t)(first + off) * (slen + 1), row_bytes,
                                  cudaMemcpyHostToDevice, l.stream));
         mark(0);
-        cudaError_t e = launch_pack(plan.layout, l.d_rows.p, slen, n, l.d_packed.p, ctx->sm_count, l.stream);
-        if (e != cudaSuccess) return fail(BGSA_ERR_CUDA, "pack kernel launch failed: %s", cudaGetErrorString(e));
-        g_launches.fetch_add(1);
+        if (!fused) {
+            cudaError_t e = launch_pack(plan.layout, l.d_rows.p, slen, n, l.d_packed.p, ctx->sm_count, l.stream);
+            if (e != cudaSuccess) return fail(BGSA_ERR_CUDA, "pack kernel launch failed: %s", cudaGetErrorString(e));
+            g_launches.fetch_add(1);
+        }
         mark(1);
         if (li != 0) CUDA_TRY(cudaStreamWaitEvent(l.stream, job.tab_ready, 0));
         rc = run_align(plan, ctx->sm_count, d_tab, static_cast<unsigned long long *>(l.d_counters.p), n_queries, query_len,
-                       l.d_packed.p, slen, n, l.d_results.p, n, l.stream);
+                       fused ? nullptr : l.d_packed.p, slen, n, l.d_results.p, n, l.stream, nullptr, fused ? l.d_rows.p : nullptr);
         if (rc) return rc;
         mark(2);
         // device -> host: [query][subject] rows into the caller's (possibly wider) result matrix
