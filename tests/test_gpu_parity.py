@@ -472,3 +472,17 @@ def test_rows_device_entry_other_algorithms(B):
         B.align_rows_device(B.Params.default(algo), q, d_rows.data_ptr(), 170, 3001, d_res.data_ptr(), 3001)
         torch.cuda.synchronize()
         assert (d_res.cpu().numpy().view(np.int16).reshape(2, 3001) == R.oracle_batch(oalgo, q, s)).all(), algo
+
+
+def test_device_management_entries(B):
+    import ctypes as C
+    import torch
+    lib = B.load()
+    n = torch.cuda.device_count()
+    assert lib.bgsa_init_devices(n) == 0                       # all contexts, in parallel
+    assert lib.bgsa_init_devices(0) == 1 and lib.bgsa_init_devices(n + 1) == 1      # BGSA_ERR_ARG
+    assert b"requested" in lib.bgsa_last_error()
+    node = C.c_int(-7)
+    assert lib.bgsa_bind_thread_to_device(0, C.byref(node)) == 0 and node.value >= -1
+    q, s = synth.make("C2", 500)                                # the thread is still usable afterwards
+    assert (B.align_batch(B.Params.default(B.MYERS_GLOBAL), q, s) == expect(0, q, s)).all()
