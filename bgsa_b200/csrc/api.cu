@@ -499,8 +499,11 @@ int bgsa_align_batch_submit(const bgsa_params_t *p, const char *queries, int n_q
     // every warp starts on its own work unit, so a chunk of a whole number of quanta keeps all warps busy for the
     // same number of rounds.  Small chunks let the kernels follow the H2D stream closely (only the first chunk's
     // copy and the last chunk's kernel are exposed): aim at ~16 chunks, never below one quantum or 4 MB of rows.
+    // banded Myers on short rows: one fused kernel per chunk (ASCII tile -> shared-memory strip -> band), no pack launch
+    const bool fused = plan.algo == BGSA_BANDED_MYERS && banded_fused_fits(slen);
     long long quantum = 0;
-    rc = run_align(plan, ctx->sm_count, d_tab, nullptr, n_queries, query_len, nullptr, slen, 0, nullptr, 0, nullptr, &quantum);
+    rc = run_align(plan, ctx->sm_count, d_tab, nullptr, n_queries, query_len, nullptr, slen, 0, nullptr, 0, nullptr, &quantum,
+                   fused ? static_cast<const void *>(&quantum) : nullptr);      // (dry run: the pointer only selects the kernel)
     if (rc) return rc;
     if (quantum < kTileSubjects) quantum = kTileSubjects;
     static const int kChunks = getenv("BGSA_CHUNKS") ? atoi(getenv("BGSA_CHUNKS")) : 16;   // tuning knob
@@ -519,8 +522,6 @@ int bgsa_align_batch_submit(const bgsa_params_t *p, const char *queries, int n_q
         job.trace.clear();
         CUDA_TRY(cudaEventRecord(job.t0, job.lane[0].stream));
     }
-    // banded Myers on short rows: one fused kernel per chunk (ASCII tile -> shared-memory strip -> band), no pack launch
-    const bool fused = plan.algo == BGSA_BANDED_MYERS && banded_fused_fits(slen);
     int li = 0;
     for (int64_t off = 0, step = first_chunk; off < count; off += step, step = chunk, li = (li + 1) % kLanesPerJob) {
         const int64_t n = count - off < step ? count - off : step;
