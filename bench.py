@@ -210,11 +210,9 @@ def main():
     config["host_numa_node"] = numa_node
     params = B.Params.default(wl["algo"], **wl["kw"])
     # every rank owns its own contiguous shard of equal size (weak scaling; no data-path collective)
-    query, _ = synth.make(wl["cfg"], 1)
-    _, subjects = synth.make(wl["cfg"], count)
-    if world > 1:
-        # decorrelate the shards: same generator, rank-specific row order
-        subjects = np.ascontiguousarray(subjects[np.random.default_rng(cfg["seed"] * 1000 + rank).permutation(subjects.shape[0])])
+    # (rank r > 0 draws its own subjects from the same recipe -- same query, same mix -- so that every GPU does the
+    #  same kind of work as the single GPU of the N = 1 run)
+    query, subjects = synth.make(wl["cfg"], count, shard=rank)
     ns = subjects.shape[0]
     cells = float(qlen) * slen * ns
     esize = 1 if wl["algo"] == B.BANDED_MYERS else 2

@@ -37,14 +37,17 @@ CONFIGS = {
 }
 
 
-def make(name: str, count: int | None = None):
+def make(name: str, count: int | None = None, shard: int = 0):
     """Returns (query rows [1, qlen+1], subject rows [count, slen+1]) for a config; `count`
     truncates the subject set (the generator is sequential, so the first `count` subjects of the
-    full set are reproduced only for the iid configs C2/C4/C5; C3 keeps its 50/50 mix at any size)."""
+    full set are reproduced only for the iid configs C2/C4/C5; C3 keeps its 50/50 mix at any size).
+    shard > 0 draws the subjects from a different stream (the query stays the config's)."""
     cfg = CONFIGS[name]
     n = cfg["count"] if count is None else count
     rng = np.random.default_rng(cfg["seed"])
     query = _rows(rng, 1, cfg["qlen"])
+    if shard:      # another shard of the same workload (multi-GPU weak scaling): same query, same recipe, fresh subjects
+        rng = np.random.default_rng(cfg["seed"] * 1000 + shard)
     if name == "C3":
         half = n // 2
         similar = _mutated(rng, query[0, : cfg["qlen"]], half, 8)
