@@ -19,6 +19,11 @@
  *   bgsa_align_device           the generated kernels align_cpu/align_sse/align_avx/align_mic
  *                               (original/BGSA_CPU/align_core.h:8 and twins), batched.
  *   align_core.h (this dir)     the per-chunk kernel symbols themselves, for unmodified callers.
+ *
+ * Threading: every entry point may be called from any host thread; bgsa_last_error() is thread-local.  One job at a time
+ * per (device, slot): a second bgsa_align_batch_submit on the same pair before bgsa_align_batch_wait returned would reuse
+ * the pair's streams and buffers (the reference's a/b buffers have the same rule, thread.c:35-170).  Different devices and
+ * the two slots of a device are independent.  bgsa_align_peq_chunk serialises its callers (it is called from an OpenMP team).
  */
 #ifndef BGSA_B200_H
 #define BGSA_B200_H
