@@ -22,6 +22,7 @@ import numpy as np
 __all__ = [
     "MYERS_GLOBAL", "MYERS_SEMIGLOBAL", "BANDED_MYERS", "BITPAL_PACKED", "BITPAL_NONPACKED", "BITPAL_PACKED_SEMIGLOBAL",
     "BgsaError", "Params", "SeqT", "load", "lib_path", "align_batch", "result_dtype", "to_codes",
+    "align_batch_submit", "align_batch_wait", "init_devices",
     "packed_bytes", "pack_subjects_device", "align_device", "align_rows_device", "int_peak", "bind_thread_to_device", "launch_count", "kernel_name", "supported",
 ]
 
@@ -169,6 +170,29 @@ def align_batch(params: Params, queries: np.ndarray, subjects: np.ndarray, first
     _check(lib.bgsa_align_batch(C.byref(params), qc.ctypes.data, nq, qlen, C.byref(seq), first, count,
                                 out.ctypes.data, out.strides[0] // out.itemsize, device))
     return out
+
+
+def init_devices(n_devices: int) -> None:
+    """Creates the contexts (streams, events) of devices 0..n-1 in parallel (bgsa_init_devices)."""
+    _check(load().bgsa_init_devices(n_devices))
+
+
+def align_batch_submit(params: Params, queries: np.ndarray, subjects: np.ndarray, first: int, count: int, out: np.ndarray,
+                       device: int = 0, slot: int = 0) -> None:
+    """Asynchronous half of align_batch (bgsa_align_batch_submit): enqueues H2D + kernels + D2H of subjects
+    [first, first+count) on `device` and returns.  `subjects` and `out` must stay alive (and should be pinned) until
+    align_batch_wait(device, slot).  out: [nq, >= count] scores, written at column 0.. -- the host-side mirror of one
+    device's share in cal_mic.c:459-481."""
+    qc = np.ascontiguousarray(to_codes(np.asarray(queries, dtype=np.uint8)))
+    seq = make_seq(subjects)
+    nq, qlen = qc.shape[0], qc.shape[1] - 1
+    assert out.dtype == result_dtype(params.algo) and out.shape[0] == nq and out.shape[1] >= count
+    _check(load().bgsa_align_batch_submit(C.byref(params), qc.ctypes.data, nq, qlen, C.byref(seq), first, count,
+                                          out.ctypes.data, out.strides[0] // out.itemsize, device, slot))
+
+
+def align_batch_wait(device: int = 0, slot: int = 0) -> None:
+    _check(load().bgsa_align_batch_wait(device, slot))
 
 
 def packed_bytes(subject_len: int, count: int) -> int:

@@ -1,5 +1,6 @@
 // inst_misc.cu -- banded kernel instances, pack / unpeq kernels, algorithm dispatchers and the
 // INT32-pipe throughput probe.
+#include <cstdio>
 #include <cstdlib>
 
 #include "banded.cuh"
@@ -42,16 +43,47 @@ cudaError_t launch_bitpal_nonpacked(int scheme, int K, int L, const LaunchArgs &
 }
 
 // ---- banded ------------------------------------------------------------------------------------
+// Row block after which a tile parks its survivors (banded.cuh "Survivor compaction"): the block by whose end a subject
+// unrelated to the query has certainly run out of its error budget -- it collects about one error per 1.5 rows after
+// the first e rows, and dies at 2e+2.  -1: no such block before the last one (short queries), or compaction switched off
+// (BGSA_BANDED_REFILL=off).  BGSA_BANDED_REFILL=<block>[,<max alive>] overrides (A/B measurements).
+static void banded_refill_policy(int qlen, int e, int *block, int *max_alive) {
+    const int nblocks = (qlen + 31) / 32;
+    int P = (e + 3 * (e + 1) + 31) / 32 - 1, alive = 24;
+    const char *env = getenv("BGSA_BANDED_REFILL");          // (read per launch: the tests vary it)
+    if (env) {
+        if (env[0] == 'o') P = -1;
+        else { int b = 0, m = 0; const int n = sscanf(env, "%d,%d", &b, &m); if (n >= 1) P = b; if (n >= 2) alive = m; }
+    }
+    if (P < 0 || P + 1 >= nblocks || qlen >= 65536) P = -1;
+    if (alive < 1) alive = 1;
+    if (alive > 32) alive = 32;
+    *block = P; *max_alive = alive;
+}
+
 template <bool WIDE, bool FUSED>
 static cudaError_t launch_banded_t(const LaunchArgs &a, const uint8_t *ascii, const void *d_rows_table, int e) {
     constexpr int THREADS = 128;
     const bool multi = a.n_queries > 1;
     auto kern = multi ? banded_kernel<WIDE, true, FUSED, THREADS> : banded_kernel<WIDE, false, FUSED, THREADS>;
-    const size_t smem = FUSED ? sizeof(uint32_t) * (size_t)pack_warp_words(a.ps.slen + 1, 1) * (THREADS / 32) : 0;
-    if (smem > 48 * 1024) return cudaErrorInvalidValue;        // callers route long rows to pack + align
-    int occ = 0;                                               // (cheap; depends on smem for FUSED)
-    cudaError_t err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, smem);
+    int refill_block, refill_max_alive;
+    banded_refill_policy(a.qlen, e, &refill_block, &refill_max_alive);
+    auto smem_of = [&](int block) { return sizeof(uint32_t) * (size_t)banded_warp_words(WIDE, FUSED, a.ps.slen, block) * (THREADS / 32); };
+    const size_t smem_plain = smem_of(-1);
+    if (smem_plain > 48 * 1024) return cudaErrorInvalidValue;   // callers route long rows to pack + align
+    int occ = 0;                                               // (cheap; depends on smem)
+    cudaError_t err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, smem_plain);
     if (err != cudaSuccess) return err;
+    size_t smem = smem_plain;
+    if (refill_block >= 0) {                                    // the survivor ring must not cost occupancy
+        int occ_ring = 0;
+        const size_t smem_ring = smem_of(refill_block);
+        if (smem_ring <= 48 * 1024) {
+            err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_ring, kern, THREADS, smem_ring);
+            if (err != cudaSuccess) return err;
+        }
+        if (occ_ring >= occ && occ_ring > 0) smem = smem_ring; else refill_block = -1;
+    }
     if (occ < 1) occ = 1;
     if (a.dry_run) {
         if (a.resident_subjects) *a.resident_subjects = (long long)a.sm_count * occ * (THREADS / 32) * 32;
@@ -65,7 +97,8 @@ static cudaError_t launch_banded_t(const LaunchArgs &a, const uint8_t *ascii, co
     if (want > resident) want = resident;
     if (want < 1) want = 1;
     kern<<<(unsigned)want, THREADS, smem, a.stream>>>(a.ps, ascii, static_cast<const BandedRow *>(d_rows_table), nq, a.qlen, e,
-                                                      static_cast<int8_t *>(a.d_results), a.result_stride, a.d_counters);
+                                                      static_cast<int8_t *>(a.d_results), a.result_stride, a.d_counters,
+                                                      refill_block, refill_max_alive);
     return cudaGetLastError();
 }
 cudaError_t launch_banded(const LaunchArgs &a, const void *d_rows_table, int e) {

@@ -22,7 +22,7 @@
 
 // BitPAl non-packed (one vector per delta value: register hungry, so few words per lane)
 #define BGSA_BITPAL_NONPACKED_INSTANCES(X)                                                   \
-    X(1, 1) X(2, 1) X(2, 2) X(2, 4) X(2, 8) X(2, 16) X(2, 32) X(3, 32) X(5, 32)
+    X(1, 1) X(2, 1) X(3, 1) X(4, 1) X(5, 1) X(3, 2) X(2, 2) X(2, 4) X(2, 8) X(2, 16) X(2, 32) X(3, 32) X(5, 32)
 
 // Scoring schemes (match, mismatch, gap) with a kernel instance; index = scheme id.
 // Scheme 0 is the one the reference checks in (original/BGSA_AVX512/align_core.c:13-15).

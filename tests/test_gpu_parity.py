@@ -146,6 +146,41 @@ def test_banded_vs_oracle(B, L, e):
         assert (exp == 127).any() and (exp < 127).any()
 
 
+@pytest.mark.parametrize("L,e,policy", [(100, 5, None), (100, 5, "off"), (100, 5, "0,32"), (100, 5, "0,8"), (100, 5, "1,24"),
+                                        (150, 5, "2,32"), (250, 7, None), (250, 15, "1,32"), (100, 20, "0,32"), (333, 31, "3,30"),
+                                        (640, 20, None), (96, 5, "1,32"), (97, 5, "1,32")])
+def test_banded_shuffled_survivor_compaction(B, L, e, policy, monkeypatch):
+    """Near-matches and unrelated subjects INTERLEAVED: the kernel parks the survivors of a tile in a shared-memory
+    ring after row block P and finishes them 32 at a time (banded.cuh "Survivor compaction"), so the scores -- and,
+    bench.py workload C3s, the speed -- must not depend on the order of the subjects.  Every policy (block, max alive;
+    off) must give the oracle's scores, through the packed-tile kernel, the fused ASCII kernel and with several
+    queries (the ring is flushed when a warp moves on to another query)."""
+    import torch
+    if policy is None:
+        monkeypatch.delenv("BGSA_BANDED_REFILL", raising=False)
+    else:
+        monkeypatch.setenv("BGSA_BANDED_REFILL", policy)
+    rng = np.random.default_rng(L * 101 + e)
+    n = 6000 if L <= 150 else 1500
+    q = R.random_rows(rng, 3, L)
+    s = np.concatenate([R.mutate_rows(rng, q[0, :L], n // 3, 2 * e + 2), R.indel_rows(rng, q[1, :L], n // 6, e + 3),
+                        R.mutate_rows(rng, q[2, :L], n // 6, e), R.random_rows(rng, n - n // 3 - 2 * (n // 6), L)])
+    s = np.ascontiguousarray(s[rng.permutation(n)])
+    s[rng.integers(0, n, 3), rng.integers(0, L, 3)] = ord("N")          # a few tiles take the N path (never parked)
+    exp = expect(2, q, s, threshold=e)
+    p = B.Params.default(B.BANDED_MYERS, threshold=e)
+    for nq in (1, 3):
+        got = B.align_batch(p, q[:nq], s)                                # fused kernel (rows <= ~950 bases)
+        assert (got == exp[:nq]).all(), ("fused", L, e, policy, nq)
+        d_rows = torch.from_numpy(s.reshape(-1)).cuda()
+        d_packed = torch.empty(B.packed_bytes(L, n), dtype=torch.uint8, device="cuda")
+        d_res = torch.full((nq * n,), 99, dtype=torch.int8, device="cuda")
+        B.pack_subjects_device(p, d_rows.data_ptr(), L, n, d_packed.data_ptr())
+        B.align_device(p, q[:nq], d_packed.data_ptr(), L, n, d_res.data_ptr(), n)
+        torch.cuda.synchronize()
+        assert (d_res.cpu().numpy().reshape(nq, n) == exp[:nq]).all(), ("packed", L, e, policy, nq)
+
+
 # ---- edge cases ------------------------------------------------------------------------------------
 def test_empty_and_tiny_batches(B):
     rng = np.random.default_rng(1)

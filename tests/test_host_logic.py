@@ -90,6 +90,29 @@ def test_kernel_selection_matches_baseline_configs():
     assert B.kernel_name(B.Params.default(B.BANDED_MYERS, threshold=31), 100, 100) == "banded_kernel<u64>"
 
 
+def test_sass_carry_chains_and_budget():
+    """Build-time guard for the hardware carry chains (bgsa_common.cuh add_chain: consecutive add.cc / addc.cc asm
+    statements rely on nothing clobbering CC.CF in between): in the SASS of the thread-per-subject kernels every
+    K-word add must be exactly one IADD3 that starts a carry chain plus K-1 links (IADD3.X, or IMAD.X for a dead
+    carry-out) -- Myers: one chain per column, BitPAl packed (2,-3,-5): one per high class (NH = 5).  A toolkit that
+    breaks or pads the chains changes these counts.  Also pins the ALU-pipe instruction budget per word-column that
+    DESIGN.md and bench.py's roofline.frac_sass quote (tools/sass_budget.py)."""
+    _ensure_built()
+    sys.path.insert(0, str(ROOT / "tools"))
+    import sass_budget as SB
+    funcs = SB.sass_functions(ROOT / "bgsa_b200" / "libbgsa_b200.so")
+    expect = {"C2_bitpal_packed_K5": (5, 5, 70.0), "C4_myers_semi_K32": (1, 32, 10.6), "myers150_K5": (1, 5, 10.8),
+              "bitpal_nonpacked_150": (5, 5, 175.0)}
+    for name, (chains, K, max_alu_per_word) in expect.items():
+        r = SB.analyse(name, SB.KERNELS[name], funcs, None)
+        assert "error" not in r, (name, r)
+        assert r["carry_chain_starts_per_column"] == chains, (name, r)
+        assert r["carry_chain_links_per_column"] == chains * (K - 1), (name, r)
+        assert r["alu_per_word_column"] <= max_alu_per_word, (name, r["alu_per_word_column"])
+    r = SB.analyse("C3_banded_fused", SB.KERNELS["C3_banded_fused"], funcs, None)
+    assert r["alu_per_column"] <= 13.5, r          # 13 per band row: no predicated-off N-path instructions in the common path
+
+
 @pytest.mark.parametrize("mode", [0, 1])
 def test_myers_columns_on_host(sim, mode):
     rng = np.random.default_rng(100 + mode)

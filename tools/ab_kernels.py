@@ -43,11 +43,19 @@ def run(name, algo, ql, sl, ns, reps=7, **kw):
         torch.cuda.synchronize()
         if r >= 2:
             tp.append(ev[0].elapsed_time(ev[1])); ta.append(ev[1].elapsed_time(ev[2]))
+    tf = []
+    if algo == B.BANDED_MYERS:       # the fused kernel (ASCII rows in, one launch)
+        for r in range(reps):
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+            ev[0].record(); B.align_rows_device(p, qq, d_rows.data_ptr(), sl, ns, d_res.data_ptr(), ns, 0, st); ev[1].record()
+            torch.cuda.synchronize()
+            if r >= 2:
+                tf.append(ev[0].elapsed_time(ev[1]))
     crc = zlib.crc32(d_res.cpu().numpy().tobytes())
     cells = ql * sl * ns
     a, pk = float(np.median(ta)), float(np.median(tp))
     print(f"{tag} {name:10s} {B.kernel_name(p, ql, sl):52s} pack {pk:8.3f} ms  align {a:9.3f} ms  "
-          f"{cells / a / 1e6:10.1f} GCUPS  crc {crc:08x}", flush=True)
+          f"{cells / a / 1e6:10.1f} GCUPS  crc {crc:08x}" + (f"  fused {float(np.median(tf)):8.3f} ms {cells / float(np.median(tf)) / 1e6:10.1f} GCUPS" if tf else ""), flush=True)
 
 
 ops, mhz = B.int_peak(0)
@@ -57,6 +65,7 @@ run("myers150", B.MYERS_GLOBAL, 150, 150, 1_000_000)
 run("myers64", B.MYERS_GLOBAL, 64, 64, 2_000_000)
 run("C1big", B.MYERS_GLOBAL, 500, 500, 300_000)
 run("C3", B.BANDED_MYERS, 100, 100, 10_000_000, threshold=5)
+run("C3s", B.BANDED_MYERS, 100, 100, 10_000_000, threshold=5)
 run("C4", B.MYERS_SEMIGLOBAL, 1000, 1000, 300_000)
 run("C5", B.BITPAL_PACKED, 5000, 5000, 8192, reps=4)
 run("C2np", B.BITPAL_NONPACKED, 150, 150, 300_000)

@@ -32,9 +32,16 @@ CONFIGS = {
     # name: (algo name, query_len, subject_len, full subject count, seed, extra)
     "C2": dict(algo="bitpal_packed", qlen=150, slen=150, count=1_000_000, seed=12345),
     "C3": dict(algo="banded", qlen=100, slen=100, count=10_000_000, seed=777, threshold=5),
+    # C3 with its two halves interleaved at random: the same subjects, order-independence check of the banded early exit
+    "C3s": dict(algo="banded", qlen=100, slen=100, count=10_000_000, seed=777, threshold=5),
     "C4": dict(algo="myers_semiglobal", qlen=1000, slen=1000, count=1_000_000, seed=4),
     "C5": dict(algo="bitpal_packed", qlen=5000, slen=5000, count=1_000_000, seed=5),
 }
+
+
+def shuffled(subjects, name: str = "C3s"):
+    """The rows of `subjects` in the (seeded) random order of config `name`."""
+    return np.ascontiguousarray(subjects[np.random.default_rng(CONFIGS[name]["seed"] + 1).permutation(subjects.shape[0])])
 
 
 def make(name: str, count: int | None = None, shard: int = 0):
@@ -48,11 +55,13 @@ def make(name: str, count: int | None = None, shard: int = 0):
     query = _rows(rng, 1, cfg["qlen"])
     if shard:      # another shard of the same workload (multi-GPU weak scaling): same query, same recipe, fresh subjects
         rng = np.random.default_rng(cfg["seed"] * 1000 + shard)
-    if name == "C3":
+    if name in ("C3", "C3s"):
         half = n // 2
         similar = _mutated(rng, query[0, : cfg["qlen"]], half, 8)
         rest = _rows(rng, n - half, cfg["slen"])
         subjects = np.concatenate([similar, rest])
+        if name == "C3s":
+            subjects = shuffled(subjects, name)
     elif name == "C4":
         subjects = _rows(rng, n, cfg["slen"])
         # 1 % planted query substrings so that the semi-global minima vary
