@@ -175,13 +175,29 @@ struct Job {
     cudaEvent_t t0 = nullptr;            // trace origin
     std::vector<ChunkTrace> trace;
 };
+// State of the device-resident entry points (bgsa_align_device / bgsa_align_rows_device), ONE PER CALLER STREAM: query
+// tables, work counters and the packed scratch are reused call after call, which is only safe in stream order.  Calls on
+// different streams (or from different threads on different streams) get different slots; calls on the same stream are
+// serialised by the slot's mutex while they enqueue.
+struct Resident {
+    bool used = false;
+    cudaStream_t stream = nullptr;
+    unsigned long long last_use = 0;
+    QueryCache qc;
+    Buf counters;
+    Buf packed;              // bgsa_align_rows_device: packed form of the caller's rows (algorithms without a fused kernel)
+    std::mutex mu;
+};
+constexpr int kResidentSlots = 8;
 struct DeviceCtx {
     bool ready = false;
     int sm_count = 0;
     Job job[2];
-    QueryCache resident_qc;  // bgsa_align_device / bgsa_align_rows_device (caller's stream)
-    Buf resident_counters;
-    Buf resident_packed;     // bgsa_align_rows_device: packed form of the caller's rows (algorithms without a fused kernel)
+    Resident resident[kResidentSlots];
+    std::mutex resident_mu;
+    unsigned long long resident_clock = 0;
+    Lane chunk_lane;         // bgsa_align_peq_chunk (its callers are serialised)
+    QueryCache chunk_qc;
 };
 constexpr int kMaxDevices = 64;
 DeviceCtx g_ctx[kMaxDevices];
@@ -198,9 +214,49 @@ int get_ctx(int device, DeviceCtx **out) {
             for (Lane &l : j.lane) CUDA_TRY(cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking));
             CUDA_TRY(cudaEventCreateWithFlags(&j.tab_ready, cudaEventDisableTiming));
         }
+        CUDA_TRY(cudaStreamCreateWithFlags(&c.chunk_lane.stream, cudaStreamNonBlocking));
         c.ready = true;
     }
     *out = &c;
+    return BGSA_OK;
+}
+
+// The resident slot of `stream`, locked (lk).  A stream seen for the first time takes a free slot, or the least recently
+// used one after its stream has drained.
+int get_resident(DeviceCtx *ctx, cudaStream_t stream, Resident **out, std::unique_lock<std::mutex> *lk) {
+    Resident *r = nullptr;
+    {
+        std::lock_guard<std::mutex> g(ctx->resident_mu);
+        Resident *lru = nullptr;
+        for (Resident &c : ctx->resident) {
+            if (c.used && c.stream == stream) { r = &c; break; }
+            if (!c.used) { if (!lru || lru->used) lru = &c; }
+            else if (!lru || (lru->used && c.last_use < lru->last_use)) lru = &c;
+        }
+        if (!r) {
+            r = lru;
+            if (r->used) {                                   // recycle: nothing of the old stream may still read the buffers
+                std::lock_guard<std::mutex> busy(r->mu);
+                CUDA_TRY(cudaStreamSynchronize(r->stream));
+                r->qc.key.clear();
+            }
+            r->used = true;
+            r->stream = stream;
+        }
+        r->last_use = ++ctx->resident_clock;
+    }
+    *lk = std::unique_lock<std::mutex>(r->mu);
+    *out = r;
+    return BGSA_OK;
+}
+
+// Pointers the kernels read with 16-byte vector loads / bulk copies must be aligned (a misaligned address is a sticky
+// context error, not a status code): packed tiles 256 B (make_packed_view), results to their element size.
+int check_device_pointers(const void *d_packed, const void *d_results, size_t esize) {
+    if (d_packed && (reinterpret_cast<uintptr_t>(d_packed) & 255u))
+        return fail(BGSA_ERR_ARG, "d_packed must be 256-byte aligned (cudaMalloc alignment)");
+    if (d_results && (reinterpret_cast<uintptr_t>(d_results) & (esize - 1)))
+        return fail(BGSA_ERR_ARG, "d_results must be aligned to the score size (%zu bytes)", esize);
     return BGSA_OK;
 }
 
@@ -221,7 +277,7 @@ int stage_queries(QueryCache &qc, const Plan &plan, const char *queries, int nq,
     if (plan.algo == BGSA_BANDED_MYERS) bytes = sizeof(BandedRowHost) * (size_t)nq * qlen;
     else bytes = sizeof(uint32_t) * (size_t)nq * kPeqRows * h_peq_row_stride(plan.kl.K, plan.kl.L);
     if (bytes > qc.pinned_cap) {
-        if (qc.pinned) cudaFreeHost(qc.pinned);
+        if (qc.pinned) { cudaStreamSynchronize(stream); cudaFreeHost(qc.pinned); }
         qc.pinned = nullptr; qc.pinned_cap = 0;
         CUDA_TRY(cudaMallocHost(&qc.pinned, bytes + 256));
         qc.pinned_cap = bytes + 256;
@@ -237,6 +293,7 @@ int stage_queries(QueryCache &qc, const Plan &plan, const char *queries, int nq,
             build_query_peq(row, qlen, plan.kl.K, plan.kl.L,
                             static_cast<uint32_t *>(qc.pinned) + (size_t)q * kPeqRows * h_peq_row_stride(plan.kl.K, plan.kl.L));
     }
+    qc.key.clear();                                      // whatever follows, the old tables are gone
     rc = qc.d_tab.ensure(bytes);
     if (rc) return rc;
     CUDA_TRY(cudaMemcpyAsync(qc.d_tab.p, qc.pinned, bytes, cudaMemcpyHostToDevice, stream));
@@ -417,6 +474,7 @@ int bgsa_pack_subjects_device(const bgsa_params_t *p, const void *d_rows, int su
     int rc = get_ctx(device, &ctx);
     if (rc) return rc;
     if (count == 0) return BGSA_OK;
+    if ((rc = check_device_pointers(d_packed, nullptr, 1))) return rc;
     const int layout = p->algo == BGSA_BANDED_MYERS ? LAYOUT_PLANES : LAYOUT_CODES;
     cudaError_t e = launch_pack(layout, d_rows, subject_len, count, d_packed, ctx->sm_count, static_cast<cudaStream_t>(stream));
     if (e != cudaSuccess) return fail(BGSA_ERR_CUDA, "pack kernel launch failed: %s", cudaGetErrorString(e));
@@ -435,12 +493,16 @@ int bgsa_align_device(const bgsa_params_t *p, const char *h_queries, int n_queri
     rc = get_ctx(device, &ctx);
     if (rc) return rc;
     if (count == 0 || n_queries == 0) return BGSA_OK;
+    if ((rc = check_device_pointers(d_packed, d_results, (size_t)plan.result_size))) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    Resident *res;
+    std::unique_lock<std::mutex> lk;
+    if ((rc = get_resident(ctx, st, &res, &lk))) return rc;
     const void *d_tab;
-    rc = stage_queries(ctx->resident_qc, plan, h_queries, n_queries, query_len, subject_len, st, &d_tab);
+    rc = stage_queries(res->qc, plan, h_queries, n_queries, query_len, subject_len, st, &d_tab);
     if (rc) return rc;
-    if ((rc = ctx->resident_counters.ensure(sizeof(unsigned long long) * (size_t)n_queries))) return rc;
-    return run_align(plan, ctx->sm_count, d_tab, static_cast<unsigned long long *>(ctx->resident_counters.p), n_queries,
+    if ((rc = res->counters.ensure(sizeof(unsigned long long) * (size_t)n_queries))) return rc;
+    return run_align(plan, ctx->sm_count, d_tab, static_cast<unsigned long long *>(res->counters.p), n_queries,
                      query_len, d_packed, subject_len, count, d_results, result_stride, st);
 }
 
@@ -455,26 +517,31 @@ int bgsa_align_rows_device(const bgsa_params_t *p, const char *h_queries, int n_
     rc = get_ctx(device, &ctx);
     if (rc) return rc;
     if (count == 0 || n_queries == 0) return BGSA_OK;
+    if ((rc = check_device_pointers(nullptr, d_results, (size_t)plan.result_size))) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    Resident *res;
+    std::unique_lock<std::mutex> lk;
+    if ((rc = get_resident(ctx, st, &res, &lk))) return rc;
     const void *d_tab;
-    rc = stage_queries(ctx->resident_qc, plan, h_queries, n_queries, query_len, subject_len, st, &d_tab);
+    rc = stage_queries(res->qc, plan, h_queries, n_queries, query_len, subject_len, st, &d_tab);
     if (rc) return rc;
-    if ((rc = ctx->resident_counters.ensure(sizeof(unsigned long long) * (size_t)n_queries))) return rc;
-    unsigned long long *d_counters = static_cast<unsigned long long *>(ctx->resident_counters.p);
+    if ((rc = res->counters.ensure(sizeof(unsigned long long) * (size_t)n_queries))) return rc;
+    unsigned long long *d_counters = static_cast<unsigned long long *>(res->counters.p);
     if (plan.algo == BGSA_BANDED_MYERS && banded_fused_fits(subject_len))     // ASCII in, scores out, one kernel
         return run_align(plan, ctx->sm_count, d_tab, d_counters, n_queries, query_len, nullptr, subject_len, count, d_results,
                          result_stride, st, nullptr, d_rows);
-    if ((rc = ctx->resident_packed.ensure((size_t)packed_bytes(subject_len, count)))) return rc;
-    cudaError_t e = launch_pack(plan.layout, d_rows, subject_len, count, ctx->resident_packed.p, ctx->sm_count, st);
+    if (packed_bytes(subject_len, count) > (int64_t)res->packed.cap) CUDA_TRY(cudaStreamSynchronize(st));   // the old scratch may still be read
+    if ((rc = res->packed.ensure((size_t)packed_bytes(subject_len, count)))) return rc;
+    cudaError_t e = launch_pack(plan.layout, d_rows, subject_len, count, res->packed.p, ctx->sm_count, st);
     if (e != cudaSuccess) return fail(BGSA_ERR_CUDA, "pack kernel launch failed: %s", cudaGetErrorString(e));
     g_launches.fetch_add(1);
-    return run_align(plan, ctx->sm_count, d_tab, d_counters, n_queries, query_len, ctx->resident_packed.p, subject_len, count,
+    return run_align(plan, ctx->sm_count, d_tab, d_counters, n_queries, query_len, res->packed.p, subject_len, count,
                      d_results, result_stride, st);
 }
 
-int bgsa_align_batch_submit(const bgsa_params_t *p, const char *queries, int n_queries, int query_len,
-                            const bgsa_seq_t *subjects, int64_t first, int64_t count, void *results, int64_t result_stride,
-                            int device, int slot) {
+static int submit_impl(const bgsa_params_t *p, const char *queries, int n_queries, int query_len,
+                       const bgsa_seq_t *subjects, int64_t first, int64_t count, void *results, int64_t result_stride,
+                       int device, int slot) {
     if (!subjects) return fail(BGSA_ERR_ARG, "subjects is NULL");
     Plan plan;
     int rc = make_plan(p, query_len, subjects->len, &plan);
@@ -559,6 +626,21 @@ int bgsa_align_batch_submit(const bgsa_params_t *p, const char *queries, int n_q
     return BGSA_OK;
 }
 
+int bgsa_align_batch_submit(const bgsa_params_t *p, const char *queries, int n_queries, int query_len,
+                            const bgsa_seq_t *subjects, int64_t first, int64_t count, void *results, int64_t result_stride,
+                            int device, int slot) {
+    const int rc = submit_impl(p, queries, n_queries, query_len, subjects, first, count, results, result_stride, device, slot);
+    if (rc == BGSA_ERR_CUDA || rc == BGSA_ERR_NOMEM) {
+        // A failure in the middle of the chunk loop leaves copies and kernels of the earlier chunks in flight, some of
+        // them writing into the caller's `results`: nothing may outlive the failed call, so drain the job's streams
+        // (the message of the original failure is kept).
+        if (device >= 0 && device < kMaxDevices && slot >= 0 && slot <= 1 && g_ctx[device].ready)
+            for (Lane &l : g_ctx[device].job[slot].lane) cudaStreamSynchronize(l.stream);
+        g_ctx[device >= 0 && device < kMaxDevices ? device : 0].job[slot >= 0 && slot <= 1 ? slot : 0].qc.key.clear();
+    }
+    return rc;
+}
+
 int bgsa_align_batch_wait(int device, int slot) {
     if (slot < 0 || slot > 1) return fail(BGSA_ERR_ARG, "slot must be 0 or 1");
     DeviceCtx *ctx;
@@ -605,8 +687,7 @@ int bgsa_align_peq_chunk(const bgsa_params_t *p, const char *query, int query_le
     if (n_subjects == 0) return BGSA_OK;
     static std::mutex chunk_mu;                 // the reference calls its kernel from an OpenMP team
     std::lock_guard<std::mutex> lk(chunk_mu);
-    Job &job = ctx->job[1];
-    Lane &l = job.lane[0];
+    Lane &l = ctx->chunk_lane;                  // its own stream and buffers: never collides with a slot-1 batch
     const size_t peq_bytes = (size_t)word_bytes * 5 * word_num * (size_t)n_subjects;
     const size_t esize = plan.result_size;
     if ((rc = l.d_rows.ensure(peq_bytes))) return rc;
@@ -622,7 +703,7 @@ int bgsa_align_peq_chunk(const bgsa_params_t *p, const char *query, int query_le
     std::vector<char> qrow(query, query + query_len);
     qrow.push_back('\n');
     const void *d_tab;
-    rc = stage_queries(job.qc, plan, qrow.data(), 1, query_len, subject_len, l.stream, &d_tab);
+    rc = stage_queries(ctx->chunk_qc, plan, qrow.data(), 1, query_len, subject_len, l.stream, &d_tab);
     if (rc) return rc;
     rc = run_align(plan, ctx->sm_count, d_tab, static_cast<unsigned long long *>(l.d_counters.p), 1, query_len, l.d_packed.p,
                    subject_len, n_subjects, l.d_results.p, n_subjects, l.stream);

@@ -1,6 +1,8 @@
 // launch.cuh -- host-side launch helper shared by the instance files.
 #pragma once
 
+#include <atomic>
+
 #include "align_kernel.cuh"
 
 namespace bgsa {
@@ -27,11 +29,17 @@ constexpr int kAlignCH = 4;          // 128-bit units (256 bases) per lane and s
 template <class Algo, int L, int UNROLL>
 cudaError_t launch_align(const LaunchArgs &a, typename Algo::Params prm) {
     auto kern = align_kernel<Algo, L, kAlignCH, kAlignThreads, UNROLL>;
-    static int occ = 0;
+    // resident CTAs per SM of this instance, cached PER DEVICE (contexts may differ in carve-out; first calls may race:
+    // the atomics make that benign -- every thread computes the same value)
+    static std::atomic<int> occ_cache[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int occ = occ_cache[dev & 63].load(std::memory_order_relaxed);
     if (occ == 0) {
         cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kAlignThreads, 0);
         if (e != cudaSuccess) return e;
         if (occ < 1) occ = 1;
+        occ_cache[dev & 63].store(occ, std::memory_order_relaxed);
     }
     if (a.dry_run) {
         if (a.resident_subjects) *a.resident_subjects = (long long)a.sm_count * occ * (kAlignThreads / 32) * (32 / L);

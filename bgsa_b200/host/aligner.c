@@ -71,7 +71,7 @@ static unsigned char map_char(unsigned char c) {
 }
 
 int main(int argc, char **argv) {
-    const char *file_query = NULL, *file_database = NULL, *file_result = "result.txt"; /* main.c:72-75 */
+    const char *file_query = NULL, *file_database = NULL, *file_result = "data/result.txt"; /* main.c:39 (handle_args overrides main.c:75) */
     bgsa_params_t prm;
     bgsa_params_default(&prm, BGSA_MYERS_GLOBAL);
     int algo = BGSA_MYERS_GLOBAL, ngpu = 1, have_k = 0;
@@ -128,6 +128,7 @@ int main(int argc, char **argv) {
 
     char info_name[4096];
     snprintf(info_name, sizeof(info_name), "%s.info", file_result);                /* main.c:80-87 */
+    mkdir("data", 0755);                                                           /* create_folder("data", 0755), cal_cpu.c:198 */
     FILE *fp_ref = open_file(file_query, "rb");
     FILE *fp_read = open_file(file_database, "rb");
     FILE *fp_result = open_file(file_result, "wb+");

@@ -23,7 +23,16 @@
  * Threading: every entry point may be called from any host thread; bgsa_last_error() is thread-local.  One job at a time
  * per (device, slot): a second bgsa_align_batch_submit on the same pair before bgsa_align_batch_wait returned would reuse
  * the pair's streams and buffers (the reference's a/b buffers have the same rule, thread.c:35-170).  Different devices and
- * the two slots of a device are independent.  bgsa_align_peq_chunk serialises its callers (it is called from an OpenMP team).
+ * the two slots of a device are independent.  bgsa_align_peq_chunk serialises its callers (it is called from an OpenMP team)
+ * and has its own stream and buffers.  The device-resident entries (bgsa_align_device, bgsa_align_rows_device) keep their
+ * query tables, work counters and packed scratch PER CALLER STREAM (up to 8 streams per device; a ninth recycles the
+ * least recently used slot after draining its stream): calls on different streams never share state, calls on one stream
+ * are ordered by the stream.
+ *
+ * Device pointers: d_packed must be 256-byte aligned and d_results aligned to the score size (BGSA_ERR_ARG otherwise --
+ * a misaligned vector load would be a sticky context error).  d_rows may have ANY alignment; the kernels read it in whole
+ * aligned 16-byte pieces, i.e. up to 15 bytes before its first and after its last byte inside the same 16-byte granules
+ * (never written, never across a page the range does not touch).
  */
 #ifndef BGSA_B200_H
 #define BGSA_B200_H

@@ -100,6 +100,21 @@ def test_aligner_banded_c3_slice_vs_reference_aligner(tmp_path):
         assert md5(tmp_path / "ours.txt") == md5(tmp_path / "ref.txt")
 
 
+def test_aligner_default_result_path(sample, tmp_path):
+    """Without -f the reference writes data/result.txt (+ .info) and creates ./data itself (original/BGSA_CPU/main.c:39,
+    cal_cpu.c:198); so do we, and the reference aligner run the same way leaves identical files."""
+    out = run([ALIGNER, "-q", sample / "query.txt", "-d", sample / "subject.txt"], tmp_path)
+    assert "cal GCUPS is" in out
+    assert md5(tmp_path / "data" / "result.txt") == "7253c1f2a6423aaa3e29577acc137302"
+    assert md5(tmp_path / "data" / "result.txt.info") == "210a66912c2846fdc6d3e64fa8fbe61f"
+    if (REF / "aligner_myers_cpu").exists():
+        ref_dir = tmp_path / "ref"
+        ref_dir.mkdir()
+        run([REF / "aligner_myers_cpu", "-q", sample / "query.txt", "-d", sample / "subject.txt"], ref_dir)
+        assert md5(ref_dir / "data" / "result.txt") == md5(tmp_path / "data" / "result.txt")
+        assert md5(ref_dir / "data" / "result.txt.info") == md5(tmp_path / "data" / "result.txt.info")
+
+
 def test_aligner_multi_bucket_multi_query_vs_reference_aligner(tmp_path):
     """> READ_BUCKET_SIZE (114857600 B) of subjects => 2 read buckets; 3 queries => [query][subject] per bucket."""
     need(REF / "aligner_myers_cpu")
