@@ -23,7 +23,7 @@ __all__ = [
     "MYERS_GLOBAL", "MYERS_SEMIGLOBAL", "BANDED_MYERS", "BITPAL_PACKED", "BITPAL_NONPACKED", "BITPAL_PACKED_SEMIGLOBAL",
     "BgsaError", "Params", "SeqT", "load", "lib_path", "align_batch", "result_dtype", "to_codes",
     "align_batch_submit", "align_batch_wait", "init_devices",
-    "packed_bytes", "pack_subjects_device", "align_device", "align_rows_device", "int_peak", "bind_thread_to_device", "launch_count", "kernel_name", "supported",
+    "packed_bytes", "pack_subjects_device", "pack_subjects_host", "host_pack_info", "align_device", "align_rows_device", "int_peak", "bind_thread_to_device", "launch_count", "kernel_name", "supported",
 ]
 
 MYERS_GLOBAL, MYERS_SEMIGLOBAL, BANDED_MYERS, BITPAL_PACKED, BITPAL_NONPACKED, BITPAL_PACKED_SEMIGLOBAL = range(6)
@@ -90,6 +90,8 @@ def load():
         "bgsa_bind_thread_to_device": (i32, [i32, C.POINTER(i32)]),
         "bgsa_packed_bytes": (i64, [i32, i64]),
         "bgsa_pack_subjects_device": (i32, [PP, vp, i32, i64, vp, i32, vp]),
+        "bgsa_pack_subjects_host": (i32, [PP, vp, i32, i64, vp]),
+        "bgsa_host_pack_info": (i32, [C.POINTER(i32), C.c_char_p, i32]),
         "bgsa_align_device": (i32, [PP, vp, i32, i32, vp, i32, i64, vp, i64, i32, vp]),
         "bgsa_align_rows_device": (i32, [PP, vp, i32, i32, vp, i32, i64, vp, i64, i32, vp]),
         "bgsa_launch_count": (i64, []),
@@ -108,7 +110,7 @@ EXPORTED_SYMBOLS = [
     "bgsa_version", "bgsa_last_error", "bgsa_device_count", "bgsa_init_devices", "bgsa_params_default", "bgsa_result_size", "bgsa_supported",
     "bgsa_align_batch", "bgsa_align_batch_submit", "bgsa_align_batch_wait", "bgsa_malloc_host", "bgsa_free_host",
     "bgsa_host_register", "bgsa_host_unregister", "bgsa_bind_thread_to_device",
-    "bgsa_packed_bytes", "bgsa_pack_subjects_device", "bgsa_align_device", "bgsa_align_rows_device", "bgsa_launch_count", "bgsa_kernel_name",
+    "bgsa_packed_bytes", "bgsa_pack_subjects_device", "bgsa_pack_subjects_host", "bgsa_host_pack_info", "bgsa_align_device", "bgsa_align_rows_device", "bgsa_launch_count", "bgsa_kernel_name",
     "bgsa_int_peak", "bgsa_align_peq_chunk",
 ]
 
@@ -202,6 +204,22 @@ def packed_bytes(subject_len: int, count: int) -> int:
 def pack_subjects_device(params: Params, d_rows_ptr: int, subject_len: int, count: int, d_packed_ptr: int,
                          device: int = 0, stream: int = 0) -> None:
     _check(load().bgsa_pack_subjects_device(C.byref(params), d_rows_ptr, subject_len, count, d_packed_ptr, device, stream))
+
+
+def pack_subjects_host(params: Params, subjects: np.ndarray) -> np.ndarray:
+    """ASCII rows -> packed tiles on the host cores (bgsa_pack_subjects_host); returns the packed bytes."""
+    assert subjects.dtype == np.uint8 and subjects.ndim == 2 and subjects.flags.c_contiguous
+    count, slen = subjects.shape[0], subjects.shape[1] - 1
+    out = np.zeros(packed_bytes(slen, count), dtype=np.uint8)
+    _check(load().bgsa_pack_subjects_host(C.byref(params), subjects.ctypes.data, slen, count, out.ctypes.data))
+    return out
+
+
+def host_pack_info():
+    t = C.c_int(0)
+    buf = C.create_string_buffer(32)
+    _check(load().bgsa_host_pack_info(C.byref(t), buf, 32))
+    return t.value, buf.value.decode()
 
 
 def align_device(params: Params, queries: np.ndarray, d_packed_ptr: int, subject_len: int, count: int,

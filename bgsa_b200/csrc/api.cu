@@ -17,6 +17,7 @@
 
 #include "../../include/bgsa_b200.h"
 #include "banded_host.h"
+#include "host_pack.h"
 #include "bitpal.cuh"
 #include "instances.h"
 #include "launch.cuh"
@@ -157,9 +158,26 @@ struct QueryCache {          // device copy of the query-side tables of the last
 };
 // One in-flight chunk: its own stream and device buffers, so that the H2D copy of chunk i+1
 // overlaps the kernels of chunk i and the D2H copy of chunk i-1 (three different engines).
+struct PinnedBuf {           // grow-only pinned host staging
+    void *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return BGSA_OK;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        const size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMallocHost(&p, want);
+        if (e != cudaSuccess) return fail(BGSA_ERR_NOMEM, "cudaMallocHost(%zu) failed: %s", want, cudaGetErrorString(e));
+        cap = want;
+        return BGSA_OK;
+    }
+};
 struct Lane {
     cudaStream_t stream = nullptr;
     Buf d_rows, d_packed, d_results, d_counters;
+    PinnedBuf h_packed;                  // host-packed tiles of the chunk in flight (host_pack.h)
+    cudaEvent_t staged = nullptr;        // the H2D copy out of h_packed has completed
+    bool staged_pending = false;
 };
 constexpr int kLanesPerJob = 3;
 // A "job" = one bgsa_align_batch_submit() call: the subject range is cut into chunks that
@@ -482,6 +500,24 @@ int bgsa_pack_subjects_device(const bgsa_params_t *p, const void *d_rows, int su
     return BGSA_OK;
 }
 
+static bool host_pack_chunk(int layout, const uint8_t *rows, int slen, int64_t n, void *h_packed);
+
+int bgsa_pack_subjects_host(const bgsa_params_t *p, const void *rows, int subject_len, int64_t count, void *packed) {
+    if (!p || (!rows && count > 0) || (!packed && count > 0) || subject_len <= 0 || count < 0)
+        return fail(BGSA_ERR_ARG, "bgsa_pack_subjects_host: bad argument");
+    if (count == 0) return BGSA_OK;
+    const int layout = p->algo == BGSA_BANDED_MYERS ? LAYOUT_PLANES : LAYOUT_CODES;
+    // (the N plane of tiles without an N is left untouched, exactly as the device pack kernels leave it)
+    host_pack_chunk(layout, static_cast<const uint8_t *>(rows), subject_len, count, packed);
+    return BGSA_OK;
+}
+
+int bgsa_host_pack_info(int *threads, char *isa, int isa_len) {
+    if (threads) *threads = HostPool::instance().threads();
+    if (isa && isa_len > 0) snprintf(isa, (size_t)isa_len, "%s", host_pack_isa());
+    return BGSA_OK;
+}
+
 int bgsa_align_device(const bgsa_params_t *p, const char *h_queries, int n_queries, int query_len, const void *d_packed,
                       int subject_len, int64_t count, void *d_results, int64_t result_stride, int device, void *stream) {
     Plan plan;
@@ -539,6 +575,54 @@ int bgsa_align_rows_device(const bgsa_params_t *p, const char *h_queries, int n_
                      d_results, result_stride, st);
 }
 
+// ---- optional host-side pack (host_pack.h) -----------------------------------------------------------------------------
+// Worth it when the PCIe copy of the ASCII rows, not the kernel, bounds the batch and the host threads can encode faster
+// than the link moves bytes: compares the predicted time per subject of both pipelines.  BGSA_HOST_PACK=0 / 1 forces it.
+static bool decide_host_pack(const Plan &plan, int nq, int qlen, int slen, int64_t count, const void *rows) {
+    if (const char *env = getenv("BGSA_HOST_PACK")) {
+        if (env[0] == '0') return false;
+        if (env[0] == '1') return true;
+    }
+    if (count < 8192) return false;
+    const double bytes = (double)slen + 1.0;
+    const double words = (double)plan.kl.K * (plan.kl.L > 0 ? plan.kl.L : 1);
+    double instr;                                        // ALU lane-instructions per (query, subject)
+    switch (plan.algo) {
+        case BGSA_MYERS_GLOBAL: case BGSA_MYERS_SEMIGLOBAL: instr = (double)slen * words * 10.2; break;
+        case BGSA_BITPAL_PACKED: case BGSA_BITPAL_PACKED_SEMIGLOBAL: instr = (double)slen * words * 67.0; break;
+        case BGSA_BITPAL_NONPACKED: instr = (double)slen * words * 165.0; break;
+        default: instr = (double)qlen * 13.0 * 0.7 + 250.0; break;      // banded: ~2/3 of the rows on average
+    }
+    const double t_kernel = nq * instr / 18.0e12;
+    cudaPointerAttributes attr;
+    bool pinned = true;
+    if (cudaPointerGetAttributes(&attr, rows) == cudaSuccess) pinned = attr.type != cudaMemoryTypeUnregistered;
+    else cudaGetLastError();
+    const double t_h2d = bytes / (pinned ? 52e9 : 9e9);  // measured: 55 GB/s pinned, ~10 GB/s pageable (driver staging)
+    static const double per_thread = getenv("BGSA_HOST_PACK_RATE") ? atof(getenv("BGSA_HOST_PACK_RATE")) * 1e9 : 4.0e9;
+    const double t_pack = bytes / (HostPool::instance().threads() * per_thread);
+    const double with = std::max(t_pack, std::max(t_kernel, t_h2d / 4.0));
+    const double without = std::max(t_h2d, t_kernel);
+    return with < 0.85 * without;
+}
+
+struct HostPackTask { int layout; const uint8_t *rows; int slen; int64_t count; void *packed; int64_t ntiles, grain; std::atomic<int> any_n; };
+static void host_pack_block(int64_t i, void *arg) {
+    HostPackTask *t = static_cast<HostPackTask *>(arg);
+    const int64_t t0 = i * t->grain, t1 = std::min(t->ntiles, t0 + t->grain);
+    if (host_pack_tiles(t->layout, t->rows, t->slen, t->count, t->packed, t0, t1)) t->any_n.store(1);
+}
+// packs `n` rows into `h_packed` (tile layout) with the pool; returns whether any tile holds an N
+static bool host_pack_chunk(int layout, const uint8_t *rows, int slen, int64_t n, void *h_packed) {
+    HostPackTask t;
+    t.layout = layout; t.rows = rows; t.slen = slen; t.count = n; t.packed = h_packed;
+    t.ntiles = (n + kTileSubjects - 1) / kTileSubjects;
+    t.grain = std::max<int64_t>(1, (96 << 10) / (kTileSubjects * ((int64_t)slen + 1)));
+    t.any_n.store(0);
+    HostPool::instance().parallel_for((t.ntiles + t.grain - 1) / t.grain, host_pack_block, &t);
+    return t.any_n.load() != 0;
+}
+
 static int submit_impl(const bgsa_params_t *p, const char *queries, int n_queries, int query_len,
                        const bgsa_seq_t *subjects, int64_t first, int64_t count, void *results, int64_t result_stride,
                        int device, int slot) {
@@ -567,7 +651,8 @@ static int submit_impl(const bgsa_params_t *p, const char *queries, int n_querie
     // same number of rounds.  Small chunks let the kernels follow the H2D stream closely (only the first chunk's
     // copy and the last chunk's kernel are exposed): aim at ~16 chunks, never below one quantum or 4 MB of rows.
     // banded Myers on short rows: one fused kernel per chunk (ASCII tile -> shared-memory strip -> band), no pack launch
-    const bool fused = plan.algo == BGSA_BANDED_MYERS && banded_fused_fits(slen);
+    const bool host_pack = decide_host_pack(plan, n_queries, query_len, slen, count, subjects->content + (size_t)first * (slen + 1));
+    const bool fused = !host_pack && plan.algo == BGSA_BANDED_MYERS && banded_fused_fits(slen);
     long long quantum = 0;
     rc = run_align(plan, ctx->sm_count, d_tab, nullptr, n_queries, query_len, nullptr, slen, 0, nullptr, 0, nullptr, &quantum,
                    fused ? static_cast<const void *>(&quantum) : nullptr);      // (dry run: the pointer only selects the kernel)
@@ -598,15 +683,36 @@ static int submit_impl(const bgsa_params_t *p, const char *queries, int n_querie
             if (kTrace && cudaEventCreate(&tr.ev[i]) == cudaSuccess) cudaEventRecord(tr.ev[i], l.stream);
         };
         const size_t row_bytes = (size_t)n * (slen + 1);
-        if ((rc = l.d_rows.ensure(row_bytes + 16))) return rc;
+        if (!host_pack && (rc = l.d_rows.ensure(row_bytes + 16))) return rc;
         if (!fused && (rc = l.d_packed.ensure((size_t)packed_bytes(slen, n)))) return rc;
         if ((rc = l.d_results.ensure(esize * (size_t)n_queries * (size_t)n))) return rc;
         if ((rc = l.d_counters.ensure(sizeof(unsigned long long) * (size_t)n_queries))) return rc;
-        // host -> device: the ASCII rows exactly as file.c:44-115 left them
-        CUDA_TRY(cudaMemcpyAsync(l.d_rows.p, subjects->content + (size_t)(first + off) * (slen + 1), row_bytes,
-                                 cudaMemcpyHostToDevice, l.stream));
+        if (host_pack) {
+            // host threads encode the chunk into pinned staging (the kernels of the previous chunks run meanwhile), then a
+            // quarter of the bytes crosses the link: the codes, the per-tile N flags and -- only if some tile has an N -- the N plane
+            const size_t pbytes = (size_t)packed_bytes(slen, n);
+            if (l.staged_pending) { CUDA_TRY(cudaEventSynchronize(l.staged)); l.staged_pending = false; }
+            if ((rc = l.h_packed.ensure(pbytes))) return rc;
+            const bool any_n = host_pack_chunk(plan.layout, reinterpret_cast<const uint8_t *>(subjects->content) + (size_t)(first + off) * (slen + 1),
+                                               slen, n, l.h_packed.p);
+            const PackedSubjects hv = make_packed_view(l.h_packed.p, slen, n);
+            const char *hb = static_cast<const char *>(l.h_packed.p);
+            char *db = static_cast<char *>(l.d_packed.p);
+            const size_t codes_bytes = (size_t)hv.ntiles * hv.ku * 32 * sizeof(uint4);
+            const size_t nm_off = (size_t)(reinterpret_cast<const char *>(hv.nmask) - hb), fl_off = (size_t)(reinterpret_cast<const char *>(hv.tile_has_n) - hb);
+            CUDA_TRY(cudaMemcpyAsync(db, hb, codes_bytes, cudaMemcpyHostToDevice, l.stream));
+            CUDA_TRY(cudaMemcpyAsync(db + fl_off, hb + fl_off, (size_t)hv.ntiles, cudaMemcpyHostToDevice, l.stream));
+            if (any_n) CUDA_TRY(cudaMemcpyAsync(db + nm_off, hb + nm_off, (size_t)hv.ntiles * hv.kn * 32 * sizeof(uint32_t), cudaMemcpyHostToDevice, l.stream));
+            if (!l.staged) CUDA_TRY(cudaEventCreateWithFlags(&l.staged, cudaEventDisableTiming));
+            CUDA_TRY(cudaEventRecord(l.staged, l.stream));
+            l.staged_pending = true;
+        } else {
+            // host -> device: the ASCII rows exactly as file.c:44-115 left them
+            CUDA_TRY(cudaMemcpyAsync(l.d_rows.p, subjects->content + (size_t)(first + off) * (slen + 1), row_bytes,
+                                     cudaMemcpyHostToDevice, l.stream));
+        }
         mark(0);
-        if (!fused) {
+        if (!fused && !host_pack) {
             cudaError_t e = launch_pack(plan.layout, l.d_rows.p, slen, n, l.d_packed.p, ctx->sm_count, l.stream);
             if (e != cudaSuccess) return fail(BGSA_ERR_CUDA, "pack kernel launch failed: %s", cudaGetErrorString(e));
             g_launches.fetch_add(1);

@@ -141,6 +141,17 @@ int64_t bgsa_packed_bytes(int subject_len, int64_t count);
  * void* (NULL = default stream). */
 int bgsa_pack_subjects_device(const bgsa_params_t *p, const void *d_rows, int subject_len, int64_t count,
                               void *d_packed, int device, void *stream);
+/* The same encoding on the HOST cores (no GPU involved): `rows` and `packed` are host pointers, `packed` has
+ * bgsa_packed_bytes() bytes and the layout bgsa_align_device consumes once copied to the device -- a database can be packed
+ * once and kept (a quarter of the text's size).  Runs on the library's worker pool (BGSA_HOST_THREADS, default: all cores
+ * / BGSA_HOST_GPUS).  bgsa_align_batch_submit uses the same code by itself when the PCIe copy of the ASCII rows, not the
+ * kernel, would bound the batch and the host threads can encode faster than the link moves bytes (short reads;
+ * BGSA_HOST_PACK=0/1 forces the choice) -- the GPU-era counterpart of the reference's OpenMP Peq build
+ * (cpu_handle_reads, original/BGSA_CPU/global.c:25-70).  The N plane of a tile without 'N' is left unwritten, exactly as
+ * the device pack kernels leave it (the per-tile flag says whether it is read). */
+int bgsa_pack_subjects_host(const bgsa_params_t *p, const void *rows, int subject_len, int64_t count, void *packed);
+/* threads of the worker pool and the encoder in use ("avx2" or "scalar"). */
+int bgsa_host_pack_info(int *threads, char *isa, int isa_len);
 /* h_queries: host code rows as above; d_results: device [query][count] scores. */
 int bgsa_align_device(const bgsa_params_t *p, const char *h_queries, int n_queries, int query_len,
                       const void *d_packed, int subject_len, int64_t count,

@@ -96,6 +96,39 @@ def read_rows(path) -> np.ndarray:
     return arr.reshape(-1, length + 1).copy()
 
 
+def numpy_pack(rows, layout):
+    """rows [n, slen+1] ASCII -> (codes uint32 [ntiles, ku, 32, 4], nmask uint32 [ntiles, kn, 32], has_n [ntiles])."""
+    n, slen = rows.shape[0], rows.shape[1] - 1
+    ntiles, ku, kn = (n + 31) // 32, (slen + 63) // 64, (slen + 31) // 32
+    code = np.zeros(256, dtype=np.uint64)
+    code[ord("C")], code[ord("G")], code[ord("T")] = 1, 2, 3
+    c = np.zeros((ntiles * 32, ku * 64), dtype=np.uint64)
+    c[:n, :slen] = code[rows[:, :slen]]
+    isn = np.zeros((ntiles * 32, kn * 32), dtype=np.uint64)
+    isn[:n, :slen] = rows[:, :slen] == ord("N")
+    if layout == 0:      # base i of a unit at bits 2*(i%16) of word i/16
+        w = (c.reshape(ntiles, 32, ku, 4, 16) << (2 * np.arange(16, dtype=np.uint64))).sum(-1)
+    else:                # x,y = low/high planes of bases 0..31, z,w = of bases 32..63
+        b = c.reshape(ntiles, 32, ku, 2, 32)
+        lo = ((b & 1) << np.arange(32, dtype=np.uint64)).sum(-1)
+        hi = ((b >> 1) << np.arange(32, dtype=np.uint64)).sum(-1)
+        w = np.stack([lo[..., 0], hi[..., 0], lo[..., 1], hi[..., 1]], axis=-1)
+    codes = w.transpose(0, 2, 1, 3).astype(np.uint32)
+    nm = (isn.reshape(ntiles, 32, kn, 32) << np.arange(32, dtype=np.uint64)).sum(-1).transpose(0, 2, 1).astype(np.uint32)
+    return codes, nm, isn.reshape(ntiles, -1).any(axis=1)
+
+
+def split_packed(raw: np.ndarray, slen: int, n: int):
+    """The three regions of a packed buffer (csrc/bgsa_common.cuh make_packed_view): codes, N plane, per-tile flags."""
+    ntiles, ku, kn = (n + 31) // 32, (slen + 63) // 64, (slen + 31) // 32
+    up = lambda x: (x + 255) // 256 * 256      # noqa: E731
+    codes = raw[: ntiles * ku * 512].view(np.uint32).reshape(ntiles, ku, 32, 4)
+    o1 = up(ntiles * ku * 512)
+    nm = raw[o1: o1 + ntiles * kn * 128].view(np.uint32).reshape(ntiles, kn, 32)
+    flags = raw[o1 + up(ntiles * kn * 128): o1 + up(ntiles * kn * 128) + ntiles]
+    return codes, nm, flags
+
+
 # ------------------------------------------------------------------------------------------
 # oracle (our restatement)
 # ------------------------------------------------------------------------------------------

@@ -310,26 +310,7 @@ def test_device_resident_api_matches_host_api(B):
 
 
 # ---- pack kernels: the packed tile layout itself (csrc/bgsa_common.cuh), against a numpy packer -----
-def _numpy_pack(rows, layout):
-    """rows [n, slen+1] ASCII -> (codes uint32 [ntiles, ku, 32, 4], nmask uint32 [ntiles, kn, 32], has_n [ntiles])."""
-    n, slen = rows.shape[0], rows.shape[1] - 1
-    ntiles, ku, kn = (n + 31) // 32, (slen + 63) // 64, (slen + 31) // 32
-    code = np.zeros(256, dtype=np.uint64)
-    code[ord("C")], code[ord("G")], code[ord("T")] = 1, 2, 3
-    c = np.zeros((ntiles * 32, ku * 64), dtype=np.uint64)
-    c[:n, :slen] = code[rows[:, :slen]]
-    isn = np.zeros((ntiles * 32, kn * 32), dtype=np.uint64)
-    isn[:n, :slen] = rows[:, :slen] == ord("N")
-    if layout == 0:      # base i of a unit at bits 2*(i%16) of word i/16
-        w = (c.reshape(ntiles, 32, ku, 4, 16) << (2 * np.arange(16, dtype=np.uint64))).sum(-1)
-    else:                # x,y = low/high planes of bases 0..31, z,w = of bases 32..63
-        b = c.reshape(ntiles, 32, ku, 2, 32)
-        lo = ((b & 1) << np.arange(32, dtype=np.uint64)).sum(-1)
-        hi = ((b >> 1) << np.arange(32, dtype=np.uint64)).sum(-1)
-        w = np.stack([lo[..., 0], hi[..., 0], lo[..., 1], hi[..., 1]], axis=-1)
-    codes = w.transpose(0, 2, 1, 3).astype(np.uint32)
-    nm = (isn.reshape(ntiles, 32, kn, 32) << np.arange(32, dtype=np.uint64)).sum(-1).transpose(0, 2, 1).astype(np.uint32)
-    return codes, nm, isn.reshape(ntiles, -1).any(axis=1)
+_numpy_pack = R.numpy_pack
 
 
 @pytest.mark.parametrize("slen,n", [(150, 1000), (100, 4099), (1000, 130), (15, 77), (16, 64), (31, 33), (127, 97), (511, 65),
@@ -507,6 +488,97 @@ def test_rows_device_entry_other_algorithms(B):
         B.align_rows_device(B.Params.default(algo), q, d_rows.data_ptr(), 170, 3001, d_res.data_ptr(), 3001)
         torch.cuda.synchronize()
         assert (d_res.cpu().numpy().view(np.int16).reshape(2, 3001) == R.oracle_batch(oalgo, q, s)).all(), algo
+
+
+@pytest.mark.parametrize("force", ["1", "0"])
+def test_batch_entry_host_pack_front_end(B, force, monkeypatch):
+    """bgsa_align_batch with the subjects encoded by the host threads (BGSA_HOST_PACK=1: csrc/host_pack.cpp, a quarter of
+    the bytes over PCIe) and by the device pack kernel (=0) give the same scores as the oracle: every algorithm, rows with
+    N / arbitrary bytes, pageable (unpinned) subject memory, a sub-range that does not start on a tile, several queries,
+    more subjects than one chunk."""
+    monkeypatch.setenv("BGSA_HOST_PACK", force)
+    rng = np.random.default_rng(4242)
+    q = R.random_rows(rng, 2, 150, with_n=0.01)
+    s = R.random_rows(rng, 70_001, 150, with_n=0.001)
+    junk = rng.random(s[:, :150].shape) < 0.0005
+    s[:, :150][junk] = rng.integers(0, 256, size=int(junk.sum()), dtype=np.uint8)
+    s[5, :150] = q[0, :150]
+    for algo, oalgo in ((B.MYERS_GLOBAL, 0), (B.MYERS_SEMIGLOBAL, 1), (B.BITPAL_PACKED, 3), (B.BITPAL_NONPACKED, 3), (B.BITPAL_PACKED_SEMIGLOBAL, 5)):
+        p = B.Params.default(algo)
+        exp = R.oracle_batch(oalgo, q, s)
+        assert (B.align_batch(p, q, s) == exp).all(), (algo, force)
+        assert (B.align_batch(p, q, s, first=37, count=50_003) == exp[:, 37:37 + 50_003]).all(), (algo, force)
+    qb = R.random_rows(rng, 2, 100)
+    sb = np.concatenate([R.mutate_rows(rng, qb[0, :100], 40_000, 10), R.random_rows(rng, 30_001, 100, with_n=0.001)])
+    sb = np.ascontiguousarray(sb[rng.permutation(sb.shape[0])])
+    for e in (5, 20):
+        pb = B.Params.default(B.BANDED_MYERS, threshold=e)
+        expb = R.oracle_batch(R.ALGO_BANDED, qb, sb, e=e)
+        assert (B.align_batch(pb, qb, sb) == expb).all(), (e, force)
+        assert (B.align_batch(pb, qb, sb, first=33, count=60_000) == expb[:, 33:33 + 60_000]).all(), (e, force)
+    ql = R.random_rows(rng, 1, 2000); sl = R.random_rows(rng, 9_000, 1200)          # a wavefront instance, long rows
+    assert (B.align_batch(B.Params.default(B.BITPAL_PACKED), ql, sl) == R.oracle_batch(3, ql, sl)).all()
+
+
+def test_resident_entries_concurrent_streams_and_alignment(B):
+    """bgsa_align_device from several host threads on several streams at once, each with its OWN queries: the
+    query tables, work counters and packed scratch are per caller stream, so nothing is shared.  Misaligned
+    device pointers are rejected with BGSA_ERR_ARG instead of faulting the context."""
+    import threading
+    import torch
+    rng = np.random.default_rng(2024)
+    n, L = 20000, 150
+    s = R.random_rows(rng, n, L)
+    p = B.Params.default(B.MYERS_GLOBAL)
+    d_rows = torch.from_numpy(s.reshape(-1)).cuda()
+    d_packed = torch.empty(B.packed_bytes(L, n), dtype=torch.uint8, device="cuda")
+    B.pack_subjects_device(p, d_rows.data_ptr(), L, n, d_packed.data_ptr())
+    torch.cuda.synchronize()
+    nthreads, reps = 4, 6
+    queries = [R.random_rows(rng, 1 + t % 2, L) for t in range(nthreads)]
+    want = [R.oracle_batch(R.ALGO_MYERS_GLOBAL, q, s) for q in queries]
+    errors = []
+
+    def worker(t):
+        try:
+            torch.cuda.set_device(0)
+            stream = torch.cuda.Stream()
+            nq = queries[t].shape[0]
+            d_res = torch.zeros(nq * n, dtype=torch.int16, device="cuda")
+            for r in range(reps):
+                algo_p = p if r % 2 == 0 else B.Params.default(B.BITPAL_PACKED)
+                exp = want[t] if r % 2 == 0 else R.oracle_batch(R.ALGO_BITPAL_PACKED, queries[t], s)
+                if r % 3 == 2:     # the rows entry too (packs into the stream's own scratch)
+                    B.align_rows_device(algo_p, queries[t], d_rows.data_ptr(), L, n, d_res.data_ptr(), n, 0, stream.cuda_stream)
+                else:
+                    B.align_device(algo_p, queries[t], d_packed.data_ptr(), L, n, d_res.data_ptr(), n, 0, stream.cuda_stream)
+                stream.synchronize()
+                if not (d_res.cpu().numpy().reshape(nq, n) == exp).all():
+                    errors.append((t, r))
+        except Exception as exc:      # noqa: BLE001
+            errors.append((t, repr(exc)))
+
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(nthreads)]
+    [t.start() for t in threads]
+    [t.join() for t in threads]
+    assert not errors, errors
+    # more streams than slots: recycling keeps working
+    for i in range(12):
+        st = torch.cuda.Stream()
+        d_res = torch.zeros(n, dtype=torch.int16, device="cuda")
+        B.align_device(p, queries[0][:1], d_packed.data_ptr(), L, n, d_res.data_ptr(), n, 0, st.cuda_stream)
+        st.synchronize()
+        assert (d_res.cpu().numpy() == want[0][0]).all()
+    d_res = torch.zeros(n + 8, dtype=torch.int16, device="cuda")
+    with pytest.raises(B.BgsaError) as ei:
+        B.align_device(p, queries[0][:1], d_packed.data_ptr() + 16, L, n - 32, d_res.data_ptr(), n)
+    assert ei.value.code == 1
+    with pytest.raises(B.BgsaError) as ei:
+        B.align_device(p, queries[0][:1], d_packed.data_ptr(), L, n, d_res.data_ptr() + 1, n)
+    assert ei.value.code == 1
+    B.align_device(p, queries[0][:1], d_packed.data_ptr(), L, n, d_res.data_ptr() + 2, n)      # element-aligned is enough
+    torch.cuda.synchronize()
+    assert (d_res.cpu().numpy()[1:n + 1] == want[0][0]).all()
 
 
 def test_device_management_entries(B):
