@@ -185,7 +185,7 @@ constexpr int kLanesPerJob = 3;
 // reference's a/b ping-pong buffers (cal_cpu.c:258-267, thread.c:35-170).
 // BGSA_TRACE=1: per-chunk device timeline (ms since submit) printed to stderr by bgsa_align_batch_wait --
 // the GPU-side counterpart of the reference's read/mem/cal/write timers (cal_cpu.c:459-475).
-struct ChunkTrace { int64_t off, n; int lane; cudaEvent_t ev[4]; };     // after H2D, pack, align, D2H
+struct ChunkTrace { int64_t off, n; int lane; cudaEvent_t ev[4]; int host_packed; };     // after H2D, pack, align, D2H
 struct Job {
     Lane lane[kLanesPerJob];
     QueryCache qc;
@@ -576,14 +576,20 @@ int bgsa_align_rows_device(const bgsa_params_t *p, const char *h_queries, int n_
 }
 
 // ---- optional host-side pack (host_pack.h) -----------------------------------------------------------------------------
-// Worth it when the PCIe copy of the ASCII rows, not the kernel, bounds the batch and the host threads can encode faster
-// than the link moves bytes: compares the predicted time per subject of both pipelines.  BGSA_HOST_PACK=0 / 1 forces it.
-static bool decide_host_pack(const Plan &plan, int nq, int qlen, int slen, int64_t count, const void *rows) {
+// Per job: NEVER (the kernel, not the link, bounds the batch: long sequences, expensive scoring), ALWAYS (pageable subject
+// memory, where the ASCII copy crawls at ~10 GB/s through the driver's staging buffers; or forced), or HYBRID: the PCIe
+// link and the host threads work side by side -- a chunk goes over the link as ASCII (device pack) whenever the link would
+// otherwise run dry while the threads encode, else the threads encode it and a quarter of the bytes is shipped.
+// BGSA_HOST_PACK=0 / 1 forces never / always; =2 forces hybrid.
+enum HostPackMode { HP_NEVER = 0, HP_ALWAYS = 1, HP_HYBRID = 2 };
+constexpr double kPcieBytesPerS = 52e9;     // measured H2D rate of pinned rows on this platform (55 GB/s peak)
+static HostPackMode decide_host_pack(const Plan &plan, int nq, int qlen, int slen, int64_t count, const void *rows) {
     if (const char *env = getenv("BGSA_HOST_PACK")) {
-        if (env[0] == '0') return false;
-        if (env[0] == '1') return true;
+        if (env[0] == '0') return HP_NEVER;
+        if (env[0] == '1') return HP_ALWAYS;
+        if (env[0] == '2') return HP_HYBRID;
     }
-    if (count < 8192) return false;
+    if (count < 8192) return HP_NEVER;
     const double bytes = (double)slen + 1.0;
     const double words = (double)plan.kl.K * (plan.kl.L > 0 ? plan.kl.L : 1);
     double instr;                                        // ALU lane-instructions per (query, subject)
@@ -598,12 +604,17 @@ static bool decide_host_pack(const Plan &plan, int nq, int qlen, int slen, int64
     bool pinned = true;
     if (cudaPointerGetAttributes(&attr, rows) == cudaSuccess) pinned = attr.type != cudaMemoryTypeUnregistered;
     else cudaGetLastError();
-    const double t_h2d = bytes / (pinned ? 52e9 : 9e9);  // measured: 55 GB/s pinned, ~10 GB/s pageable (driver staging)
-    static const double per_thread = getenv("BGSA_HOST_PACK_RATE") ? atof(getenv("BGSA_HOST_PACK_RATE")) * 1e9 : 4.0e9;
-    const double t_pack = bytes / (HostPool::instance().threads() * per_thread);
-    const double with = std::max(t_pack, std::max(t_kernel, t_h2d / 4.0));
-    const double without = std::max(t_h2d, t_kernel);
-    return with < 0.85 * without;
+    const double t_pack = bytes / (HostPool::instance().threads() * 4.4e9);     // measured: 4.4-5 GB/s per thread inside the pipeline (DRAM-bound)
+    const double t_link = bytes / kPcieBytesPerS;
+    if (!pinned) return std::max(t_pack, t_kernel) < 0.9 * std::max(bytes / 9e9, t_kernel) ? HP_ALWAYS : HP_NEVER;
+    if (t_pack <= 0.9 * t_kernel) return HP_ALWAYS;                               // the threads stay ahead of the kernel: the link is nearly free
+    if (t_kernel > 1.15 * t_link) return HP_NEVER;                                // they cannot, and the link hides behind the kernel anyway
+    return t_pack < 4.0 * t_link ? HP_HYBRID : HP_NEVER;                          // threads too few to matter: leave them alone
+}
+static double host_now_s() {
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
 }
 
 struct HostPackTask { int layout; const uint8_t *rows; int slen; int64_t count; void *packed; int64_t ntiles, grain; std::atomic<int> any_n; };
@@ -651,11 +662,11 @@ static int submit_impl(const bgsa_params_t *p, const char *queries, int n_querie
     // same number of rounds.  Small chunks let the kernels follow the H2D stream closely (only the first chunk's
     // copy and the last chunk's kernel are exposed): aim at ~16 chunks, never below one quantum or 4 MB of rows.
     // banded Myers on short rows: one fused kernel per chunk (ASCII tile -> shared-memory strip -> band), no pack launch
-    const bool host_pack = decide_host_pack(plan, n_queries, query_len, slen, count, subjects->content + (size_t)first * (slen + 1));
-    const bool fused = !host_pack && plan.algo == BGSA_BANDED_MYERS && banded_fused_fits(slen);
+    const HostPackMode hp_mode = decide_host_pack(plan, n_queries, query_len, slen, count, subjects->content + (size_t)first * (slen + 1));
+    const bool can_fuse = plan.algo == BGSA_BANDED_MYERS && banded_fused_fits(slen);      // chunks that arrive as ASCII
     long long quantum = 0;
     rc = run_align(plan, ctx->sm_count, d_tab, nullptr, n_queries, query_len, nullptr, slen, 0, nullptr, 0, nullptr, &quantum,
-                   fused ? static_cast<const void *>(&quantum) : nullptr);      // (dry run: the pointer only selects the kernel)
+                   (can_fuse && hp_mode != HP_ALWAYS) ? static_cast<const void *>(&quantum) : nullptr);   // (dry run: the pointer only selects the kernel)
     if (rc) return rc;
     if (quantum < kTileSubjects) quantum = kTileSubjects;
     static const int kChunks = getenv("BGSA_CHUNKS") ? atoi(getenv("BGSA_CHUNKS")) : 16;   // tuning knob
@@ -675,10 +686,19 @@ static int submit_impl(const bgsa_params_t *p, const char *queries, int n_querie
         CUDA_TRY(cudaEventRecord(job.t0, job.lane[0].stream));
     }
     int li = 0;
+    // hybrid bookkeeping (host clock): when the link will have drained what has been queued on it, and the threads' measured rate
+    double link_free = host_now_s(), pack_rate = HostPool::instance().threads() * 4.0e9;
     for (int64_t off = 0, step = first_chunk; off < count; off += step, step = chunk, li = (li + 1) % kLanesPerJob) {
         const int64_t n = count - off < step ? count - off : step;
         Lane &l = job.lane[li];
-        ChunkTrace tr{off, n, li, {nullptr, nullptr, nullptr, nullptr}};
+        bool host_pack = hp_mode == HP_ALWAYS;
+        if (hp_mode == HP_HYBRID) {
+            // would the link still be busy by the time the threads had encoded this chunk?  then encode; else feed the link
+            const double backlog = link_free - host_now_s();
+            host_pack = backlog > 0.5 * (double)n * (slen + 1) / pack_rate;
+        }
+        const bool fused = can_fuse && !host_pack;
+        ChunkTrace tr{off, n, li, {nullptr, nullptr, nullptr, nullptr}, host_pack ? 1 : 0};
         auto mark = [&](int i) {
             if (kTrace && cudaEventCreate(&tr.ev[i]) == cudaSuccess) cudaEventRecord(tr.ev[i], l.stream);
         };
@@ -693,8 +713,12 @@ static int submit_impl(const bgsa_params_t *p, const char *queries, int n_querie
             const size_t pbytes = (size_t)packed_bytes(slen, n);
             if (l.staged_pending) { CUDA_TRY(cudaEventSynchronize(l.staged)); l.staged_pending = false; }
             if ((rc = l.h_packed.ensure(pbytes))) return rc;
+            const double t_pack0 = host_now_s();
             const bool any_n = host_pack_chunk(plan.layout, reinterpret_cast<const uint8_t *>(subjects->content) + (size_t)(first + off) * (slen + 1),
                                                slen, n, l.h_packed.p);
+            const double t_pack1 = host_now_s();
+            if (t_pack1 > t_pack0) pack_rate = 0.5 * pack_rate + 0.5 * (double)row_bytes / (t_pack1 - t_pack0);
+            link_free = std::max(link_free, t_pack1) + (double)row_bytes / 4.0 / kPcieBytesPerS;
             const PackedSubjects hv = make_packed_view(l.h_packed.p, slen, n);
             const char *hb = static_cast<const char *>(l.h_packed.p);
             char *db = static_cast<char *>(l.d_packed.p);
@@ -710,6 +734,7 @@ static int submit_impl(const bgsa_params_t *p, const char *queries, int n_querie
             // host -> device: the ASCII rows exactly as file.c:44-115 left them
             CUDA_TRY(cudaMemcpyAsync(l.d_rows.p, subjects->content + (size_t)(first + off) * (slen + 1), row_bytes,
                                      cudaMemcpyHostToDevice, l.stream));
+            link_free = std::max(link_free, host_now_s()) + (double)row_bytes / kPcieBytesPerS;
         }
         mark(0);
         if (!fused && !host_pack) {
@@ -762,8 +787,8 @@ int bgsa_align_batch_wait(int device, int slot) {
             for (int i = 0; i < 4; i++) {
                 if (c.ev[i]) { cudaEventElapsedTime(&t[i], job.t0, c.ev[i]); cudaEventDestroy(c.ev[i]); }
             }
-            fprintf(stderr, "[bgsa trace]   %10lld %9lld %d   %8.3f %8.3f %8.3f %8.3f\n", (long long)c.off, (long long)c.n, c.lane,
-                    t[0], t[1], t[2], t[3]);
+            fprintf(stderr, "[bgsa trace]   %10lld %9lld %d   %8.3f %8.3f %8.3f %8.3f  %s\n", (long long)c.off, (long long)c.n, c.lane,
+                    t[0], t[1], t[2], t[3], c.host_packed ? "host-packed" : "ascii");
         }
         job.trace.clear();
     }
