@@ -607,6 +607,8 @@ static HostPackMode decide_host_pack(const Plan &plan, int nq, int qlen, int sle
     const double t_pack = bytes / (HostPool::instance().threads() * 4.4e9);     // measured: 4.4-5 GB/s per thread inside the pipeline (DRAM-bound)
     const double t_link = bytes / kPcieBytesPerS;
     if (!pinned) return std::max(t_pack, t_kernel) < 0.9 * std::max(bytes / 9e9, t_kernel) ? HP_ALWAYS : HP_NEVER;
+    if (t_kernel > 2.0 * t_link) return HP_NEVER;                                 // the link hides behind the kernel with room to spare: leave the host
+                                                                                  // cores alone and keep the submit call asynchronous (C5: 375 ms of kernel per 12 ms of copy)
     if (t_pack <= 0.9 * t_kernel) return HP_ALWAYS;                               // the threads stay ahead of the kernel: the link is nearly free
     if (t_kernel > 1.15 * t_link) return HP_NEVER;                                // they cannot, and the link hides behind the kernel anyway
     return t_pack < 4.0 * t_link ? HP_HYBRID : HP_NEVER;                          // threads too few to matter: leave them alone

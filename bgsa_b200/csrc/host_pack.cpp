@@ -186,6 +186,8 @@ struct Batch {                       // one parallel_for in flight
     int64_t n;
     std::atomic<int64_t> next{0};
     std::atomic<int64_t> done{0};
+    int refs = 0;                    // workers that hold a pointer to this batch (guarded by Impl::mu): the batch lives on
+                                     // its caller's stack, so parallel_for must not return while a worker can still touch it
     void (*fn)(int64_t, void *);
     void *arg;
 };
@@ -210,12 +212,14 @@ struct HostPool::Impl {
             cv_work.wait(lk, [&] { return stop || !open.empty(); });
             if (stop) return;
             Batch *b = open.front();
+            b->refs++;
             lk.unlock();
             while (run_one(b)) {}
             lk.lock();
+            b->refs--;
             for (size_t k = 0; k < open.size(); k++)
                 if (open[k] == b && b->next.load() >= b->n) { open.erase(open.begin() + (long)k); break; }
-            if (b->done.load() >= b->n) cv_done.notify_all();
+            if (b->refs == 0 && b->done.load() >= b->n) cv_done.notify_all();
         }
     }
 };
@@ -226,11 +230,12 @@ static int pool_default_threads() {
         if (t >= 1) return t > 256 ? 256 : t;
     }
     // one process per GPU is the usual deployment (bench.py under torchrun, one aligner per device): leave the other
-    // ranks of the box their share of the cores.  BGSA_HOST_GPUS = GPUs sharing this host's cores (default: 1).
+    // ranks of the box their share of the cores.  BGSA_HOST_GPUS = GPUs sharing this host's cores (default: torchrun's LOCAL_WORLD_SIZE, else 1).
     unsigned hw = std::thread::hardware_concurrency();
     if (hw == 0) hw = 4;
     int share = 1;
     if (const char *g = getenv("BGSA_HOST_GPUS")) share = atoi(g) >= 1 ? atoi(g) : 1;
+    else if (const char *w = getenv("LOCAL_WORLD_SIZE")) share = atoi(w) >= 1 ? atoi(w) : 1;     // torchrun: ranks on this host
     int t = (int)hw / share;
     if (t < 1) t = 1;
     return t > 64 ? 64 : t;
@@ -265,7 +270,7 @@ void HostPool::parallel_for(int64_t n, void (*fn)(int64_t, void *), void *arg) {
     std::unique_lock<std::mutex> lk(impl_->mu);
     for (size_t k = 0; k < impl_->open.size(); k++)
         if (impl_->open[k] == &b) { impl_->open.erase(impl_->open.begin() + (long)k); break; }
-    impl_->cv_done.wait(lk, [&] { return b.done.load() >= b.n; });
+    impl_->cv_done.wait(lk, [&] { return b.refs == 0 && b.done.load() >= b.n; });
 }
 
 }  // namespace bgsa

@@ -145,6 +145,36 @@ print('ok')
     assert res.returncode == 0 and "ok" in res.stdout, res.stderr
 
 
+def test_host_pool_many_small_batches_oversubscribed():
+    """The worker pool under the conditions of one process per GPU on a shared host (bench.py --gpus N, aligner -g N):
+    far more pool threads than cores, thousands of tiny parallel_for calls from several callers at once.  A batch lives
+    on its caller's stack; a worker that still holds a pointer to it after the caller returned crashed rank 0 at N = 2
+    (use after return) -- the pool now counts the holders."""
+    code = """
+import sys, threading, numpy as np
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import bgsa_b200 as B, refutil as R
+assert B.host_pack_info()[0] == 48
+rng = np.random.default_rng(11)
+p = B.Params.default(0)
+rows = R.random_rows(rng, 96, 40)
+want = B.pack_subjects_host(p, rows).tobytes()
+bad = []
+def hammer():
+    for _ in range(1500):
+        if B.pack_subjects_host(p, rows).tobytes() != want:
+            bad.append(1)
+ts = [threading.Thread(target=hammer) for _ in range(3)]
+[t.start() for t in ts]; [t.join() for t in ts]
+assert not bad
+print('ok')
+""" % (str(ROOT), str(ROOT / "tests"))
+    _ensure_built()
+    env = dict(os.environ, BGSA_HOST_THREADS="48")
+    res = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0 and "ok" in res.stdout, (res.returncode, res.stderr[-2000:])
+
+
 def test_sass_carry_chains_and_budget():
     """Build-time guard for the hardware carry chains (bgsa_common.cuh add_chain: consecutive add.cc / addc.cc asm
     statements rely on nothing clobbering CC.CF in between): in the SASS of the thread-per-subject kernels every
