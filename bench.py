@@ -14,8 +14,10 @@ each with value / kernel time / roofline / e2e / cpu_baseline / parity.  `--only
 `--workload X` makes X the headline.
 
 Per workload:
-  value      whole-job GCUPS with the ASCII subject rows already resident in HBM (pack + align kernels, or the one
-             fused kernel), CUDA events, max over ranks; N > 1: every rank owns its own shard of equal size (weak).
+  value      whole-job GCUPS with the ASCII subject rows already resident in HBM (bgsa_align_rows_device: ONE kernel fed
+             with the ASCII rows for short reads -- align_rows_kernel, fused banded kernel -- else pack + align kernels),
+             CUDA events, max over ranks; N > 1: every rank owns its own shard of equal size (weak).  Where the one-kernel
+             path runs, "two_kernel_path" reports pack + align on packed tiles beside it.
   e2e        the same metric through the reference-facing C-ABI call bgsa_align_batch with PINNED HOST buffers:
              H2D of the rows and D2H of the scores are inside the timed region every step.
   roofline   the align kernel against the INT32 ALU-pipe roofline.  frac = SURVEY.md section 8d's MODEL instruction
@@ -62,7 +64,7 @@ WORKLOADS = {
     #       ref_sample = subjects the CPU reference is run on (timing at N = 1, parity on every rank), sass = kernel
     #       name in profiles/sass_budget.json, max_steps = cap on the timed steps when the workload is not the headline
     "C2": dict(cfg="C2", algo=3, count=1_000_000, ref="bitpal_avx512", ref_alt="bitpal_avx2", kw={}, ref_sample=1_000_000,
-               sass="C2_bitpal_packed_K5", desc="BitPAl packed M=2 I=-3 G=-5 global, 1 query x 1M synthetic 150bp subjects"),
+               sass="C2_rows_bitpal_packed_K5", desc="BitPAl packed M=2 I=-3 G=-5 global, 1 query x 1M synthetic 150bp subjects"),
     "C3": dict(cfg="C3", algo=2, count=10_000_000, ref="banded_cpu", ref_alt=None, kw={"threshold": 5}, ref_sample=1_000_000,
                sass="C3_banded_fused", desc="banded Myers verification e=5, 1 query x 10M synthetic 100bp subjects"),
     "C3s": dict(cfg="C3s", algo=2, count=10_000_000, ref="banded_cpu", ref_alt=None, kw={"threshold": 5}, ref_sample=1_000_000,
@@ -72,9 +74,9 @@ WORKLOADS = {
     "C5": dict(cfg="C5", algo=3, count=125_000, ref="bitpal_avx512", ref_alt="bitpal_avx2", kw={}, ref_sample=16_000, max_steps=5,
                sass="C5_bitpal_packed_K10_L16", desc="BitPAl global 5kbp query x 5kbp subjects, 125k subjects per GPU (1M over 8 GPUs)"),
     "myers150": dict(cfg="C2", algo=0, count=1_000_000, ref="myers_sse", ref_alt="myers_cpu", kw={}, ref_sample=1_000_000,
-                     sass="myers150_K5", desc="Myers unit-cost global, 1 query x 1M synthetic 150bp subjects"),
+                     sass="myers150_rows_K5", desc="Myers unit-cost global, 1 query x 1M synthetic 150bp subjects"),
     "C2np": dict(cfg="C2", algo=4, count=1_000_000, ref="bitpal_avx512", ref_alt="bitpal_avx2", kw={}, ref_sample=1_000_000,
-                 sass="bitpal_nonpacked_150", desc="BitPAl NON-packed M=2 I=-3 G=-5 global, 1 query x 1M synthetic 150bp subjects "
+                 sass="C2np_rows_K5", desc="BitPAl NON-packed M=2 I=-3 G=-5 global, 1 query x 1M synthetic 150bp subjects "
                                                    "(reference: the packed AVX-512 build -- same scores by definition)"),
 }
 EXTRA_ORDER = ["C3", "C3s", "C4", "C5", "myers150", "C2np"]
@@ -289,10 +291,10 @@ def measure(ctx: Ctx, name: str, steps: int, warmup: int, count: int | None, cpu
 
     # resident step: ASCII rows in HBM -> scores.  Pack + align for the transposed-DP algorithms (events around the align
     # kernel give its own duration); banded Myers is ONE fused kernel (bgsa_align_rows_device), timed as a whole.
-    fused = wl["algo"] == B.BANDED_MYERS
+    rows_kernel, fused = B.rows_kernel_name(params, qlen, slen)
 
-    def step_resident(ev=None):
-        if fused:
+    def step_resident(ev=None, one_kernel=fused):
+        if one_kernel:
             if ev:
                 ev[0].record()
             B.align_rows_device(params, query, d_rows.data_ptr(), slen, ns, d_res.data_ptr(), ns, dev, stream)
@@ -322,6 +324,25 @@ def measure(ctx: Ctx, name: str, steps: int, warmup: int, count: int | None, cpu
     launches = B.launch_count() - launches0
     ms_total = t_start.elapsed_time(t_end)
     align_ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
+    crc_resident = zlib.crc32(d_res.cpu().numpy().tobytes())
+    # the two-kernel path (pack + align on packed tiles) beside the one-kernel path, where the latter is what runs
+    two = None
+    if fused and wl["algo"] != B.BANDED_MYERS:
+        for _ in range(3):
+            step_resident(one_kernel=False)
+        evs2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        t2s, t2e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        t2s.record()
+        for i in range(steps):
+            step_resident(evs2[i], one_kernel=False)
+        t2e.record()
+        torch.cuda.synchronize()
+        ms2 = t2s.elapsed_time(t2e) / steps
+        a2 = float(np.mean([a.elapsed_time(b) for a, b in evs2]))
+        two = {"kernels": "pack_stream_kernel + " + B.kernel_name(params, qlen, slen), "ms_per_step": ms2, "align_kernel_ms": a2,
+               "value": cells / (ms2 * 1e-3) / 1e9, "value_align_kernel_only": cells / (a2 * 1e-3) / 1e9, "unit": "GCUPS (this rank)",
+               "same_scores": zlib.crc32(d_res.cpu().numpy().tobytes()) == crc_resident}
     # ---- end-to-end timing (host pinned buffers, H2D + D2H inside)
     for _ in range(3):
         step_e2e()
@@ -375,7 +396,7 @@ def measure(ctx: Ctx, name: str, steps: int, warmup: int, count: int | None, cpu
     rec = {
         "config": workload_config(name, ns),
         "value": cells * world / (ms_per_step * 1e-3) / 1e9, "unit": "GCUPS", "ms_per_step": ms_per_step, "steps": steps,
-        "kernel": B.kernel_name(params, qlen, slen) + (" (fused: ASCII tile -> shared-memory strip -> band)" if fused else ""),
+        "kernel": rows_kernel,
         "value_align_kernel_only": cells * world / (align_ms * 1e-3) / 1e9,
         "e2e": {"value": cells * world / (e2e_s / steps) / 1e9, "unit": "GCUPS", "h2d_bytes_per_step": int(ns * (slen + 1)),
                 "d2h_bytes_per_step": int(ns * esize), "ms_per_step": 1e3 * e2e_s / steps,
@@ -395,6 +416,8 @@ def measure(ctx: Ctx, name: str, steps: int, warmup: int, count: int | None, cpu
         "parity": {"against": res["variant"] if res else None, "ranks_checked": int(checked_ranks), "subjects_compared": int(compared_all),
                    "mismatches": int(mism_all), "crc32_scores_per_rank": ["%08x" % (c & 0xffffffff) for c in crcs]},
     }
+    if two is not None:
+        rec["two_kernel_path"] = two
     if res is not None and timing:
         rec["cpu_baseline"] = {"value": res["gcups_path"], "unit": "GCUPS", "cores": res["cores"], "kind": res["kind"],
                                "variant": res["variant"], "cal_only_gcups": res["gcups_cal"],
@@ -468,7 +491,8 @@ def _drive_all_devices(ctx: Ctx, c5: dict, steps: int) -> dict:
         t_one = timed([0], max(2, steps // 2))
         t_all = timed(list(range(world)), steps)
         cells_dev = float(qlen) * slen * per
-        crcs = [zlib.crc32(scores[:, f:f + c].tobytes()) for f, c in ranges]
+        # device ranges are cut on tile boundaries (sharding.py), the ranks' shards are not: compare shard by shard
+        crcs = [zlib.crc32(scores[:, r * per:(r + 1) * per].tobytes()) for r in range(world)]
         want = [c & 0xffffffff for c in c5["_crcs"]]
         out = {"workload": "C5 set, all ranks' shards concatenated", "devices": world, "subjects": total,
                "api": "one process: bgsa_align_batch_submit per device on contiguous ranges (bgsa_b200/sharding.py), "
@@ -478,11 +502,12 @@ def _drive_all_devices(ctx: Ctx, c5: dict, steps: int) -> dict:
                "e2e_one_device": {"value": cells_dev / t_one / 1e9, "unit": "GCUPS", "ms_per_step": 1e3 * t_one,
                                   "note": "the same process driving device 0 alone on its range"},
                "speedup_over_one_device": (cells_dev * world / t_all) / (cells_dev / t_one),
-               "parity": {"crc32_per_device": ["%08x" % c for c in crcs],
-                          "device_ranges_equal_to_rank_scores": int(sum(1 for a, b in zip(crcs, want) if a == b)),
+               "device_ranges": [[int(f), int(c)] for f, c in ranges],
+               "parity": {"crc32_per_shard": ["%08x" % c for c in crcs],
+                          "shards_equal_to_rank_scores": int(sum(1 for a, b in zip(crcs, want) if a == b)),
                           "of": world,
                           "note": "rank r's scores of the C5 workload above were checked against the reference on a sample "
-                                  "of its shard (workloads.C5.parity); device r's range here holds the same subjects"}}
+                                  "of its shard (workloads.C5.parity); the concatenated set holds rank r's shard at [r * per, (r + 1) * per)"}}
     return out
 
 

@@ -320,6 +320,13 @@ int stage_queries(QueryCache &qc, const Plan &plan, const char *queries, int nq,
     return BGSA_OK;
 }
 
+// ASCII rows in, scores out, ONE kernel: banded Myers with a warp strip that fits shared memory (banded.cuh FUSED), and the
+// thread-per-subject instances of the other algorithms on short rows (rows_kernel.cuh)
+bool rows_path_fused(const Plan &plan, int slen) {
+    if (plan.algo == BGSA_BANDED_MYERS) return banded_fused_fits(slen);
+    return rows_kernel_fits(plan.kl.K, plan.kl.L, slen);
+}
+
 int run_align(const Plan &plan, int sm_count, const void *d_tab, unsigned long long *d_counters, int nq, int qlen,
               const void *d_packed, int slen, int64_t count, void *d_results, int64_t result_stride, cudaStream_t stream,
               long long *resident_subjects = nullptr, const void *d_ascii_rows = nullptr) {
@@ -336,6 +343,7 @@ int run_align(const Plan &plan, int sm_count, const void *d_tab, unsigned long l
     a.d_counters = d_counters;
     a.sm_count = sm_count;
     a.stream = stream;
+    a.d_ascii = plan.algo != BGSA_BANDED_MYERS ? static_cast<const uint8_t *>(d_ascii_rows) : nullptr;   // rows kernel (rows_kernel.cuh)
     cudaError_t e;
     switch (plan.algo) {
         case BGSA_MYERS_GLOBAL:     e = launch_myers(0, plan.kl.K, plan.kl.L, a, plan.sign); break;
@@ -421,6 +429,24 @@ int bgsa_kernel_name(const bgsa_params_t *p, int query_len, int subject_len, cha
         case BGSA_BITPAL_NONPACKED: snprintf(buf, buflen, "align_kernel<BitpalNonPacked<%d,%d,%d,K=%d>,L=%d>", p->match, p->mismatch, p->gap, plan.kl.K, plan.kl.L); break;
         default: snprintf(buf, buflen, "banded_kernel<%s>", 2 * plan.e + 2 <= 32 ? "u32" : "u64"); break;
     }
+    return BGSA_OK;
+}
+
+int bgsa_rows_kernel_name(const bgsa_params_t *p, int query_len, int subject_len, char *buf, int buflen, int *fused) {
+    Plan plan;
+    int rc = make_plan(p, query_len, subject_len, &plan);
+    if (rc) return rc;
+    if (!buf || buflen <= 0) return fail(BGSA_ERR_ARG, "buf is NULL");
+    char packed[200];
+    if ((rc = bgsa_kernel_name(p, query_len, subject_len, packed, (int)sizeof(packed)))) return rc;
+    const bool one = rows_path_fused(plan, subject_len);
+    if (fused) *fused = one ? 1 : 0;
+    if (!one) { snprintf(buf, buflen, "pack_stream_kernel + %s", packed); return BGSA_OK; }
+    if (plan.algo == BGSA_BANDED_MYERS) { snprintf(buf, buflen, "%s (fused: ASCII tile -> shared-memory strip -> band)", packed); return BGSA_OK; }
+    std::string name(packed);                                  // align_kernel<Algo,L=1> -> align_rows_kernel<Algo>
+    const size_t at = name.find("align_kernel<"), l = name.rfind(",L=1>");
+    if (at != std::string::npos && l != std::string::npos) name = "align_rows_kernel<" + name.substr(at + 13, l - at - 13) + ">";
+    snprintf(buf, buflen, "%s", name.c_str());
     return BGSA_OK;
 }
 
@@ -563,7 +589,7 @@ int bgsa_align_rows_device(const bgsa_params_t *p, const char *h_queries, int n_
     if (rc) return rc;
     if ((rc = res->counters.ensure(sizeof(unsigned long long) * (size_t)n_queries))) return rc;
     unsigned long long *d_counters = static_cast<unsigned long long *>(res->counters.p);
-    if (plan.algo == BGSA_BANDED_MYERS && banded_fused_fits(subject_len))     // ASCII in, scores out, one kernel
+    if (rows_path_fused(plan, subject_len))                                  // ASCII in, scores out, one kernel
         return run_align(plan, ctx->sm_count, d_tab, d_counters, n_queries, query_len, nullptr, subject_len, count, d_results,
                          result_stride, st, nullptr, d_rows);
     if (packed_bytes(subject_len, count) > (int64_t)res->packed.cap) CUDA_TRY(cudaStreamSynchronize(st));   // the old scratch may still be read
@@ -665,7 +691,7 @@ static int submit_impl(const bgsa_params_t *p, const char *queries, int n_querie
     // copy and the last chunk's kernel are exposed): aim at ~16 chunks, never below one quantum or 4 MB of rows.
     // banded Myers on short rows: one fused kernel per chunk (ASCII tile -> shared-memory strip -> band), no pack launch
     const HostPackMode hp_mode = decide_host_pack(plan, n_queries, query_len, slen, count, subjects->content + (size_t)first * (slen + 1));
-    const bool can_fuse = plan.algo == BGSA_BANDED_MYERS && banded_fused_fits(slen);      // chunks that arrive as ASCII
+    const bool can_fuse = rows_path_fused(plan, slen);                                     // chunks that arrive as ASCII
     long long quantum = 0;
     rc = run_align(plan, ctx->sm_count, d_tab, nullptr, n_queries, query_len, nullptr, slen, 0, nullptr, 0, nullptr, &quantum,
                    (can_fuse && hp_mode != HP_ALWAYS) ? static_cast<const void *>(&quantum) : nullptr);   // (dry run: the pointer only selects the kernel)

@@ -93,6 +93,32 @@ BGSA_HD uint32_t shl1_carry(uint32_t prev, uint32_t cur) {
     return (cur << 1) | (prev >> 31);
 #endif
 }
+// (cur << 1) | BIT with a CONSTANT shift-in bit (word 0 of a vector in the thread-per-subject kernels, where nothing
+// comes from a neighbouring lane): an integer multiply-add, i.e. the FMA pipe instead of the ALU pipe that bounds the
+// kernels.  Only the plain 32-bit IMAD qualifies: IMAD.WIDE / IMAD.HI do not overlap with ALU work (tools/pipe_probe.cu,
+// profiles/r02_pipe_probe.log), so the words above word 0 -- whose shift-in bit is the top bit of the word below -- stay
+// funnel shifts.  The multiplier is a run-time value on purpose: with an immediate ptxas strength-reduces the multiply
+// to SHF/LEA, which are ALU-pipe instructions again.
+#ifndef BGSA_FMA_SHIFT0
+#define BGSA_FMA_SHIFT0 1
+#endif
+#ifdef __CUDACC__
+static __constant__ uint32_t c_bgsa_two = 2u;      // (one copy per translation unit; never written)
+#endif
+template <int BIT>
+BGSA_HD uint32_t shl1_const(uint32_t cur) {
+#ifdef __CUDA_ARCH__
+#if BGSA_FMA_SHIFT0
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(cur), "r"(c_bgsa_two), "n"(BIT));
+    return d;
+#else
+    return __funnelshift_l(BIT ? 0x80000000u : 0u, cur, 1);
+#endif
+#else
+    return (cur << 1) | (uint32_t)BIT;
+#endif
+}
 BGSA_HD int popc32(uint32_t v) {
 #ifdef __CUDA_ARCH__
     return __popc(v);

@@ -171,7 +171,9 @@ struct BitpalPacked {
                 }
                 const uint32_t sin = CARRY ? in.top() : (init_in(c) ? 0x80000000u : 0u);
 #pragma unroll
-                for (int j = 0; j < K; j++) sh[j] = shl1_carry(j ? init[j - 1] : sin, init[j]);
+                for (int j = 0; j < K; j++)
+                    sh[j] = (j == 0 && !CARRY) ? (init_in(c) ? shl1_const<1>(init[0]) : shl1_const<0>(init[0]))
+                                               : shl1_carry(j ? init[j - 1] : sin, init[j]);
                 if (CARRY) { out.push_top(init[K - 1]); in.to_cf(); }
                 add_chain<K, CARRY>(sum, sh, remain);
                 if (CARRY) out.push_cf();
@@ -224,7 +226,8 @@ struct BitpalPacked {
             uint32_t br2 = 0u;
 #pragma unroll
             for (int b = 0; b < NB; b++) {
-                const uint32_t es = shl1_carry(e_prev[b], e[b]);
+                const uint32_t es = (j == 0 && !CARRY) ? (((E0 >> b) & 1) ? shl1_const<1>(e[b]) : shl1_const<0>(e[b]))
+                                                       : shl1_carry(e_prev[b], e[b]);
                 e_prev[b] = e[b];
                 const uint32_t tb = T[b];
                 if (b == 0) { s.d[b][j] = tb ^ es; br2 = ~tb & es; }
@@ -300,13 +303,17 @@ struct BitpalNonPacked {
             const uint4 v = reinterpret_cast<const uint4 *>(row)[j];
             eq[4 * j] = v.x; eq[4 * j + 1] = v.y; eq[4 * j + 2] = v.z; eq[4 * j + 3] = v.w;
         }
-        uint32_t Z[K], remain[K];
+        // dhi = [d_p > B] is needed twice (for Z here and for max(w, d) == B at the end): OR it once
+        uint32_t Z[K], remain[K], dhi[K];
 #pragma unroll
         for (int j = 0; j < K; j++) {
-            uint32_t any = 0u;
+            uint32_t hi = 0u, lo = 0u;
 #pragma unroll
-            for (int v = 0; v < A; v++) any |= s.d[v][j];
-            Z[j] = ~any;
+            for (int v = B; v < A; v++) hi |= s.d[v][j];
+#pragma unroll
+            for (int v = 0; v < B; v++) lo |= s.d[v][j];
+            dhi[j] = hi;
+            Z[j] = ~(hi | lo);
             remain[j] = Z[j] & ~eq[j];
         }
         // DV(v, j) = [d_p == v]
@@ -340,7 +347,7 @@ struct BitpalNonPacked {
                 }
                 const uint32_t sin = CARRY ? in.top() : 0u;
 #pragma unroll
-                for (int j = 0; j < K; j++) sh[j] = shl1_carry(j ? init[j - 1] : sin, init[j]);
+                for (int j = 0; j < K; j++) sh[j] = (j == 0 && !CARRY) ? shl1_const<0>(init[0]) : shl1_carry(j ? init[j - 1] : sin, init[j]);
                 if (CARRY) { out.push_top(init[K - 1]); in.to_cf(); }
                 add_chain<K, CARRY>(sum, sh, remain);
                 if (CARRY) out.push_cf();
@@ -351,13 +358,14 @@ struct BitpalNonPacked {
                 }
             }
         }
-        uint32_t rest[K];
+        uint32_t rest[K], xhi[K];                             // xhi = [B < e_{p-1} < A], shared with X0 below
 #pragma unroll
         for (int j = 0; j < K; j++) {
-            uint32_t any = Yh[A][j];
+            uint32_t any = 0u;
 #pragma unroll
             for (int k = A - 1; k > B; k--) any |= X[k][j];
-            rest[j] = ~any;
+            xhi[j] = any;
+            rest[j] = ~(any | Yh[A][j]);
         }
         // low classes 1..B: e_p == k  <=>  y_p - d_p == k ; no propagation, plain shift
 #pragma unroll
@@ -373,16 +381,16 @@ struct BitpalNonPacked {
             const uint32_t sin = CARRY ? in.top() : 0u;
             if (CARRY) out.push_top(init[K - 1]);
 #pragma unroll
-            for (int j = 0; j < K; j++) X[k][j] = shl1_carry(j ? init[j - 1] : sin, init[j]);
+            for (int j = 0; j < K; j++) X[k][j] = (j == 0 && !CARRY) ? shl1_const<0>(init[0]) : shl1_carry(j ? init[j - 1] : sin, init[j]);
         }
 #undef DV
         // X0 = [e_{p-1} == 0]
         uint32_t X0[K];
 #pragma unroll
         for (int j = 0; j < K; j++) {
-            uint32_t any = 0u;
+            uint32_t any = xhi[j] | X[A][j];
 #pragma unroll
-            for (int k = 1; k <= A; k++) any |= X[k][j];
+            for (int k = 1; k <= B; k++) any |= X[k][j];
             X0[j] = ~any;
         }
         // Mx(v) = [max(w, d) == v]: v == A -> d==A | match ; B < v < A -> d==v & ~match ; v == B -> others
@@ -390,12 +398,10 @@ struct BitpalNonPacked {
 #pragma unroll
         for (int j = 0; j < K; j++) {
             uint32_t mx[A + 1];
-            uint32_t any = 0u;
             mx[A] = s.d[A - 1][j] | eq[j];
-            any |= mx[A];
 #pragma unroll
-            for (int v = A - 1; v > B; v--) { mx[v] = s.d[v - 1][j] & ~eq[j]; any |= mx[v]; }
-            mx[B] = ~any;
+            for (int v = A - 1; v > B; v--) mx[v] = s.d[v - 1][j] & ~eq[j];
+            mx[B] = ~(dhi[j] | eq[j]);                       // neither a match nor d > B
             uint32_t nd[A];
 #pragma unroll
             for (int k = 1; k <= A; k++) {

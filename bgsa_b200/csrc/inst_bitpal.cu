@@ -19,7 +19,7 @@ using TheScheme = Scheme<BGSA_M, BGSA_I, BGSA_G>;
 #if BGSA_PACKED == 2
 cudaError_t BGSA_CAT(launch_bitpal_semiglobal_s, BGSA_SCHEME_ID)(int K, int L, const LaunchArgs &a) {
 #define X(k, l) \
-    if (K == k && L == l) return launch_align<BitpalPacked<TheScheme, k, BITPAL_SEMIGLOBAL>, l, 2>(a, BitpalParams{0});
+    if (K == k && L == l) return launch_instance<BitpalPacked<TheScheme, k, BITPAL_SEMIGLOBAL>, l, 2>(a, BitpalParams{0});
     BGSA_BITPAL_PACKED_INSTANCES(X)
 #undef X
     return cudaErrorInvalidValue;
@@ -27,7 +27,7 @@ cudaError_t BGSA_CAT(launch_bitpal_semiglobal_s, BGSA_SCHEME_ID)(int K, int L, c
 #elif BGSA_PACKED
 cudaError_t BGSA_CAT(launch_bitpal_packed_s, BGSA_SCHEME_ID)(int K, int L, const LaunchArgs &a) {
 #define X(k, l) \
-    if (K == k && L == l) return launch_align<BitpalPacked<TheScheme, k>, l, 2>(a, BitpalParams{0});
+    if (K == k && L == l) return launch_instance<BitpalPacked<TheScheme, k>, l, 2>(a, BitpalParams{0});
     BGSA_BITPAL_PACKED_INSTANCES(X)
 #undef X
     return cudaErrorInvalidValue;
@@ -35,7 +35,7 @@ cudaError_t BGSA_CAT(launch_bitpal_packed_s, BGSA_SCHEME_ID)(int K, int L, const
 #else
 cudaError_t BGSA_CAT(launch_bitpal_nonpacked_s, BGSA_SCHEME_ID)(int K, int L, const LaunchArgs &a) {
 #define X(k, l) \
-    if (K == k && L == l) return launch_align<BitpalNonPacked<TheScheme, k>, l, 1>(a, BitpalParams{0});
+    if (K == k && L == l) return launch_instance<BitpalNonPacked<TheScheme, k>, l, 1>(a, BitpalParams{0});
     BGSA_BITPAL_NONPACKED_INSTANCES(X)
 #undef X
     return cudaErrorInvalidValue;

@@ -16,7 +16,7 @@ cudaError_t launch_myers_semiglobal(int K, int L, const LaunchArgs &a, int sign)
 #endif
     MyersParams prm{sign};
 #define X(k, l) \
-    if (K == k && L == l) return launch_align<MyersAlgo<k, BGSA_MYERS_MODE>, l, (l > 1 && k >= 24 ? 1 : (k <= 8 ? 4 : 2))>(a, prm);   // wavefront with wide lanes: unrolling only costs registers
+    if (K == k && L == l) return launch_instance<MyersAlgo<k, BGSA_MYERS_MODE>, l, (l > 1 && k >= 24 ? 1 : (k <= 8 ? 4 : 2))>(a, prm);   // wavefront with wide lanes: unrolling only costs registers
     BGSA_MYERS_INSTANCES(X)
 #undef X
     return cudaErrorInvalidValue;

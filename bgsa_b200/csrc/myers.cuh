@@ -61,8 +61,9 @@ struct MyersAlgo {
             const uint32_t d0 = lop3<(LA ^ LB) | LC>(sum, p, x);            // (sum ^ p) | x
             const uint32_t ph = lop3<LA | (0xFF ^ (LB | LC))>(m, d0, p);    // m | ~(d0 | p)
             const uint32_t mh = p & d0;
-            const uint32_t phs = shl1_carry(ph_prev, ph);
-            const uint32_t mhs = shl1_carry(mh_prev, mh);
+            // (word 0 without a lane above: the shift-in bits are the constants of the top row -- FMA pipe)
+            const uint32_t phs = (j == 0 && !CARRY) ? shl1_const<1>(ph) : shl1_carry(ph_prev, ph);
+            const uint32_t mhs = (j == 0 && !CARRY) ? shl1_const<0>(mh) : shl1_carry(mh_prev, mh);
             ph_prev = ph; mh_prev = mh;
             s.pv[j] = lop3<LA | (0xFF ^ (LB | LC))>(mhs, d0, phs);          // mhs | ~(d0 | phs)
             s.mv[j] = phs & d0;

@@ -157,11 +157,16 @@ int bgsa_align_device(const bgsa_params_t *p, const char *h_queries, int n_queri
                       const void *d_packed, int subject_len, int64_t count,
                       void *d_results, int64_t result_stride, int device, void *stream);
 /* d_rows: device pointer to ASCII rows (stride subject_len+1), as bgsa_pack_subjects_device takes them; scores to
- * d_results.  Packs into a library-owned buffer and aligns, or -- banded Myers on rows up to ~950 bases -- runs ONE
- * kernel that encodes every tile into shared memory and verifies it in place (no packed round trip through HBM). */
+ * d_results.  ONE kernel where the rows are short enough for a warp's shared-memory stage: banded Myers on rows up to ~950
+ * bases (encodes every tile into shared memory and verifies it in place), Myers / BitPAl on queries up to 256 bases and rows
+ * up to ~400 (thread per subject, match masks looked up by byte value: rows_kernel.cuh); otherwise packs into a
+ * library-owned buffer and aligns.  bgsa_rows_kernel_name tells which. */
 int bgsa_align_rows_device(const bgsa_params_t *p, const char *h_queries, int n_queries, int query_len,
                            const void *d_rows, int subject_len, int64_t count,
                            void *d_results, int64_t result_stride, int device, void *stream);
+/* Name of what bgsa_align_rows_device runs for these parameters; *fused = 1 when that is ONE kernel fed with the ASCII rows
+ * (no pack launch, no packed buffer), 0 when it is the pack kernel followed by bgsa_align_device's kernel. */
+int bgsa_rows_kernel_name(const bgsa_params_t *p, int query_len, int subject_len, char *buf, int buflen, int *fused);
 /* Number of kernel launches issued by this library since load (bench.py "gpu_launches"). */
 int64_t bgsa_launch_count(void);
 /* Name of the kernel instance bgsa_align_device would use, e.g. "bitpal_packed<2,-3,-5,K=5,L=1>". */

@@ -490,6 +490,73 @@ def test_rows_device_entry_other_algorithms(B):
         assert (d_res.cpu().numpy().view(np.int16).reshape(2, 3001) == R.oracle_batch(oalgo, q, s)).all(), algo
 
 
+@pytest.mark.parametrize("ql,sl,n", [(150, 150, 4099), (100, 100, 1000), (64, 37, 333), (256, 250, 700), (33, 400, 97), (1, 9, 70),
+                                     (150, 151, 64), (200, 135, 31), (96, 15, 65), (250, 303, 2049)])
+def test_rows_kernel_every_algorithm(B, ql, sl, n, monkeypatch):
+    """align_rows_kernel (rows_kernel.cuh): thread per subject straight from the ASCII rows, match masks looked up by byte
+    value.  Against the oracle and against the pack + align path, for every algorithm that has it; rows with N, lower
+    case and arbitrary bytes (global.c:9-15: anything else is an A), a row buffer that is not 16-byte aligned and ends
+    exactly at the end of its allocation's last row (nothing may be read past it), counts off the tile grid, one and
+    two stages per warp."""
+    import torch
+    rng = np.random.default_rng(ql * 977 + sl * 13 + n)
+    q = R.random_rows(rng, 2, ql, with_n=0.01)
+    s = R.random_rows(rng, n, sl, with_n=0.01)
+    m = min(ql, sl)
+    s[: n // 3, :m] = q[0, :m]
+    junk = rng.random(s[:, :sl].shape) < 0.004
+    s[:, :sl][junk] = rng.integers(0, 256, size=int(junk.sum()), dtype=np.uint8)
+    s[::5, sl] = 0                                            # row ends need not be newlines
+    clean = s.copy()
+    body = clean[:, :sl]
+    body[~np.isin(body, np.frombuffer(b"ACGTN", dtype=np.uint8))] = ord("A")
+    algos = [(B.MYERS_GLOBAL, 0, {}), (B.MYERS_SEMIGLOBAL, 1, {}), (B.BITPAL_PACKED, 3, {}), (B.BITPAL_NONPACKED, 3, {}),
+             (B.BITPAL_PACKED_SEMIGLOBAL, 5, {}), (B.BITPAL_PACKED, 3, dict(match=1, mismatch=-1, gap=-1)),
+             (B.BITPAL_NONPACKED, 3, dict(match=1, mismatch=-3, gap=-2))]
+    for algo, oalgo, kw in algos:
+        p = B.Params.default(algo, **kw)
+        name, fused = B.rows_kernel_name(p, ql, sl)
+        if algo == B.BITPAL_NONPACKED and ql > 160:           # the non-packed table has no thread-per-subject instance above K = 5
+            assert not fused
+            assert (B.align_batch(p, q, s) == R.oracle_batch(oalgo, q, clean, M=kw.get("match", 2), I=kw.get("mismatch", -3), G=kw.get("gap", -5))).all()
+            continue
+        assert fused and name.startswith("align_rows_kernel<"), name
+        exp = R.oracle_batch(oalgo, q, clean, M=kw.get("match", 2), I=kw.get("mismatch", -3), G=kw.get("gap", -5))
+        for shift, stages in ((0, None), (5, "1"), (9, "2")):
+            if stages is None:
+                monkeypatch.delenv("BGSA_ROWS_STAGES", raising=False)
+            else:
+                monkeypatch.setenv("BGSA_ROWS_STAGES", stages)
+            buf = torch.zeros(shift + s.size, dtype=torch.uint8, device="cuda")   # the rows end where the allocation's data ends
+            buf[shift:] = torch.from_numpy(s.reshape(-1)).cuda()
+            d_res = torch.full((2 * n,), 12345, dtype=torch.int16, device="cuda")
+            before = B.launch_count()
+            B.align_rows_device(p, q, buf.data_ptr() + shift, sl, n, d_res.data_ptr(), n)
+            torch.cuda.synchronize()
+            assert B.launch_count() - before == 1                              # one kernel, no pack launch
+            got = d_res.cpu().numpy().reshape(2, n)
+            assert (got == exp).all(), (algo, kw, ql, sl, n, shift, stages)
+        monkeypatch.delenv("BGSA_ROWS_STAGES", raising=False)
+        monkeypatch.setenv("BGSA_NO_ROWS_KERNEL", "1")                         # the same call through pack + align
+        assert not B.rows_kernel_name(p, ql, sl)[1]
+        assert (B.align_batch(p, q, s) == exp).all(), (algo, kw, "packed path")
+        monkeypatch.delenv("BGSA_NO_ROWS_KERNEL")
+        assert (B.align_batch(p, q, s) == exp).all(), (algo, kw, "batch entry, rows kernel")
+
+
+def test_rows_kernel_eligibility(B):
+    """Row pitches whose lanes would pile up on a few shared-memory banks, long rows and long queries take pack + align."""
+    p = B.Params.default(B.MYERS_GLOBAL)
+    assert B.rows_kernel_name(p, 150, 150)[1]
+    assert not B.rows_kernel_name(p, 150, 127)[1]        # pitch 128: every lane on the same bank
+    assert not B.rows_kernel_name(p, 150, 63)[1]
+    assert not B.rows_kernel_name(p, 150, 1000)[1]       # a tile does not fit the stage
+    assert not B.rows_kernel_name(p, 300, 150)[1]        # K > 8: no rows instance
+    rng = np.random.default_rng(3)
+    q = R.random_rows(rng, 1, 150); s = R.random_rows(rng, 500, 127, with_n=0.01)
+    assert (B.align_batch(p, q, s) == R.oracle_batch(0, q, s)).all()
+
+
 @pytest.mark.parametrize("force", ["1", "0"])
 def test_batch_entry_host_pack_front_end(B, force, monkeypatch):
     """bgsa_align_batch with the subjects encoded by the host threads (BGSA_HOST_PACK=1: csrc/host_pack.cpp, a quarter of

@@ -36,6 +36,9 @@ ROOT = Path(__file__).resolve().parent.parent
 #          query words per column (K), cells per column = query length of the workload)
 KERNELS = {
     "C2_bitpal_packed_K5":      (r"align_kernel<bgsa::BitpalPacked<bgsa::Scheme<2, -3, -5>, 5, 0>, 1,", None, 5, 150),
+    "C2_rows_bitpal_packed_K5": (r"align_rows_kernel<bgsa::BitpalPacked<bgsa::Scheme<2, -3, -5>, 5, 0>, 128,", None, 5, 150),
+    "myers150_rows_K5":         (r"align_rows_kernel<bgsa::MyersAlgo<5, 0>, 128,", None, 5, 150),
+    "C2np_rows_K5":             (r"align_rows_kernel<bgsa::BitpalNonPacked<bgsa::Scheme<2, -3, -5>, 5>, 128,", None, 5, 150),
     "C5_bitpal_packed_K10_L16": (r"align_kernel<bgsa::BitpalPacked<bgsa::Scheme<2, -3, -5>, 10, 0>, 16,", None, 10, 312.5),
     "C4_myers_semi_K32":        (r"align_kernel<bgsa::MyersAlgo<32, 1>, 1,", None, 32, 1000),
     "myers150_K5":              (r"align_kernel<bgsa::MyersAlgo<5, 0>, 1,", None, 5, 150),
