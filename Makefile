@@ -27,14 +27,14 @@ SCHEME_HDR := $(BUILD)/bgsa_schemes.h
 SCHEME_DEF := -include $(SCHEME_HDR)
 
 BP_OBJS := $(foreach i,$(SCHEME_IDS),$(BUILD)/inst_bp_p$(i).o $(BUILD)/inst_bp_n$(i).o $(BUILD)/inst_bp_s$(i).o)
-OBJS := $(BUILD)/api.o $(BUILD)/host_pack.o $(BUILD)/inst_misc.o $(BUILD)/inst_myers_g.o $(BUILD)/inst_myers_s.o $(BP_OBJS)
+OBJS := $(BUILD)/api.o $(BUILD)/jit.o $(BUILD)/host_pack.o $(BUILD)/inst_misc.o $(BUILD)/inst_myers_g.o $(BUILD)/inst_myers_s.o $(BP_OBJS)
 
 .PHONY: all lib tools sim clean
 all: lib tools sim
 
 lib: $(LIB)
 $(LIB): $(OBJS)
-	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -lcudart -lpthread
+	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -lcudart -lpthread -ldl
 
 $(SCHEME_HDR): Makefile | $(BUILD)
 	@echo '#define BGSA_SCHEMES(X) $(SCHEME_LIST)' > $@.tmp; cmp -s $@.tmp $@ || mv $@.tmp $@; rm -f $@.tmp
@@ -43,6 +43,12 @@ $(SCHEME_HDR): FORCE
 
 $(BUILD)/api.o: $(CSRC)/api.cu $(HDRS) $(SCHEME_HDR) | $(BUILD)
 	$(NVCC) $(NVFLAGS) $(SCHEME_DEF) -c $< -o $@
+# run-time instantiation of scoring schemes outside SCHEMES (NVRTC): the kernel headers travel inside the library
+JIT_HDRS := $(CSRC)/bgsa_common.cuh $(CSRC)/align_kernel.cuh $(CSRC)/rows_kernel.cuh $(CSRC)/bitpal.cuh
+$(BUILD)/jit_sources.inc: $(JIT_HDRS) tools/embed_sources.py | $(BUILD)
+	python tools/embed_sources.py $@ $(JIT_HDRS)
+$(BUILD)/jit.o: $(CSRC)/jit.cu $(HDRS) $(BUILD)/jit_sources.inc | $(BUILD)
+	$(NVCC) $(NVFLAGS) -I$(BUILD) -c $< -o $@
 # host-side pack (plain C++, g++; AVX2 code paths are selected at run time)
 $(BUILD)/host_pack.o: $(CSRC)/host_pack.cpp $(CSRC)/host_pack.h | $(BUILD)
 	g++ -O3 -std=c++17 -fPIC -Wall -c $< -o $@

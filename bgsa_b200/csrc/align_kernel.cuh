@@ -32,13 +32,12 @@
 // HBM traffic per subject and query: slen/4 bytes in, 2 bytes out.
 #pragma once
 
-#include <type_traits>
-
 #include "bgsa_common.cuh"
 
 namespace bgsa {
 
-struct Partial { int sum; int minpre; };   // segment sum of deltas, minimum prefix sum inside it
+struct Partial { int sum; int minpre; };
+template <bool B> struct BoolTag { static constexpr bool value = B; };     // (std::bool_constant, without the host header: NVRTC)   // segment sum of deltas, minimum prefix sum inside it
 
 // Row layout of the query Peq in shared/global memory: lane r's K words start at r * KP(K),
 // KP = K rounded up to 4 words so that every lane can use LDS.128.
@@ -127,8 +126,8 @@ align_kernel(PackedSubjects ps, const uint32_t *__restrict__ g_peq, int n_querie
                     if (decltype(checked)::value) t++;
                 }
             };
-            constexpr std::true_type kChecked{};
-            constexpr std::false_type kFree{};
+            constexpr BoolTag<true> kChecked{};
+            constexpr BoolTag<false> kFree{};
 
             for (int sg = 0; sg < nstages; sg++) {
                 // prefetch the following stage (same unit, or the first stage of the next unit)

@@ -20,6 +20,7 @@
 #include "host_pack.h"
 #include "bitpal.cuh"
 #include "instances.h"
+#include "jit.h"
 #include "launch.cuh"
 #include "pack.cuh"
 #include "query_peq.h"
@@ -81,10 +82,12 @@ int find_scheme(int M, int I, int G) {
     return -1;
 }
 
+constexpr int kSchemeJit = -2;       // Plan::scheme of a scoring scheme instantiated at run time (jit.h)
 struct Plan {
     int algo;
     KL kl;           // transposed kernels
-    int scheme;      // BitPAl
+    int scheme;      // BitPAl: id of a built-in scheme, or kSchemeJit
+    int M, I, G;     // BitPAl scores as given (0 otherwise)
     int sign;        // Myers
     int e;           // banded
     int layout;      // pack layout the kernel consumes
@@ -96,6 +99,7 @@ int make_plan(const bgsa_params_t *p, int qlen, int slen, Plan *plan) {
     if (qlen <= 0 || slen <= 0) return fail(BGSA_ERR_ARG, "sequence lengths must be positive (query %d, subject %d)", qlen, slen);
     plan->algo = p->algo;
     plan->scheme = -1;
+    plan->M = plan->I = plan->G = 0;
     plan->sign = p->myers_sign == 0 ? -1 : p->myers_sign;
     plan->e = p->threshold;
     plan->layout = LAYOUT_CODES;
@@ -112,9 +116,19 @@ int make_plan(const bgsa_params_t *p, int qlen, int slen, Plan *plan) {
         case BGSA_BITPAL_PACKED_SEMIGLOBAL:
         case BGSA_BITPAL_NONPACKED: {
             plan->scheme = find_scheme(p->match, p->mismatch, p->gap);
-            if (plan->scheme < 0)
-                return fail(BGSA_ERR_UNSUPPORTED, "BitPAl: scoring scheme (%d,%d,%d) has no kernel instance (see csrc/instances.h)",
-                            p->match, p->mismatch, p->gap);
+            plan->M = p->match; plan->I = p->mismatch; plan->G = p->gap;
+            if (plan->scheme < 0) {
+                // not one of the schemes built into the library (make SCHEMES=...): instantiate it at run time, the way the
+                // reference runs its generator for a new scheme (Main.java:240-315)
+                std::string why;
+                const int variant = p->algo == BGSA_BITPAL_NONPACKED ? 0 : (p->algo == BGSA_BITPAL_PACKED ? 1 : 2);
+                if (!jit_scheme_ok(variant, p->match, p->mismatch, p->gap, &why))
+                    return fail(BGSA_ERR_UNSUPPORTED, "BitPAl: scoring scheme (%d,%d,%d): %s", p->match, p->mismatch, p->gap, why.c_str());
+                if (!jit_available(&why))
+                    return fail(BGSA_ERR_UNSUPPORTED, "BitPAl: scoring scheme (%d,%d,%d) is not built into the library (csrc/instances.h, "
+                                "make SCHEMES=...) and cannot be instantiated at run time: %s", p->match, p->mismatch, p->gap, why.c_str());
+                plan->scheme = kSchemeJit;
+            }
             const bool ok = p->algo != BGSA_BITPAL_NONPACKED ? pick(kPackedTable, qlen, 77, 34, &plan->kl)
                                                           : pick(kNonPackedTable, qlen, 185, 45, &plan->kl);
             if (!ok) return fail(BGSA_ERR_UNSUPPORTED, "BitPAl: query length %d exceeds the largest kernel instance", qlen);
@@ -345,6 +359,17 @@ int run_align(const Plan &plan, int sm_count, const void *d_tab, unsigned long l
     a.stream = stream;
     a.d_ascii = plan.algo != BGSA_BANDED_MYERS ? static_cast<const uint8_t *>(d_ascii_rows) : nullptr;   // rows kernel (rows_kernel.cuh)
     cudaError_t e;
+    if (plan.scheme == kSchemeJit) {
+        const JitSpec spec{plan.algo == BGSA_BITPAL_NONPACKED ? 0 : (plan.algo == BGSA_BITPAL_PACKED ? 1 : 2), plan.M, plan.I, plan.G,
+                           plan.kl.K, plan.kl.L};
+        std::string err;
+        e = launch_bitpal_jit(spec, a, &err);
+        if (e != cudaSuccess)
+            return fail(err.empty() ? BGSA_ERR_CUDA : BGSA_ERR_UNSUPPORTED, "run-time instance of scheme (%d,%d,%d): %s", plan.M, plan.I,
+                        plan.G, err.empty() ? cudaGetErrorString(e) : err.c_str());
+        if (!a.dry_run) g_launches.fetch_add(1);
+        return BGSA_OK;
+    }
     switch (plan.algo) {
         case BGSA_MYERS_GLOBAL:     e = launch_myers(0, plan.kl.K, plan.kl.L, a, plan.sign); break;
         case BGSA_MYERS_SEMIGLOBAL: e = launch_myers(1, plan.kl.K, plan.kl.L, a, plan.sign); break;
@@ -429,6 +454,7 @@ int bgsa_kernel_name(const bgsa_params_t *p, int query_len, int subject_len, cha
         case BGSA_BITPAL_NONPACKED: snprintf(buf, buflen, "align_kernel<BitpalNonPacked<%d,%d,%d,K=%d>,L=%d>", p->match, p->mismatch, p->gap, plan.kl.K, plan.kl.L); break;
         default: snprintf(buf, buflen, "banded_kernel<%s>", 2 * plan.e + 2 <= 32 ? "u32" : "u64"); break;
     }
+    if (plan.scheme == kSchemeJit && strlen(buf) + 9 < (size_t)buflen) strcat(buf, " [NVRTC]");
     return BGSA_OK;
 }
 
@@ -447,6 +473,18 @@ int bgsa_rows_kernel_name(const bgsa_params_t *p, int query_len, int subject_len
     const size_t at = name.find("align_kernel<"), l = name.rfind(",L=1>");
     if (at != std::string::npos && l != std::string::npos) name = "align_rows_kernel<" + name.substr(at + 13, l - at - 13) + ">";
     snprintf(buf, buflen, "%s", name.c_str());
+    return BGSA_OK;
+}
+
+int bgsa_jit_precompile(const bgsa_params_t *p, int query_len, int subject_len) {
+    Plan plan;
+    int rc = make_plan(p, query_len, subject_len, &plan);
+    if (rc) return rc;
+    if (plan.scheme != kSchemeJit) return BGSA_OK;            // built in: nothing to do
+    const JitSpec spec{plan.algo == BGSA_BITPAL_NONPACKED ? 0 : (plan.algo == BGSA_BITPAL_PACKED ? 1 : 2), plan.M, plan.I, plan.G,
+                       plan.kl.K, plan.kl.L};
+    std::string err;
+    if (jit_precompile(spec, &err)) return fail(BGSA_ERR_UNSUPPORTED, "%s", err.c_str());
     return BGSA_OK;
 }
 

@@ -14,8 +14,23 @@
 //     per-tile flag says whether the plane needs to be looked at at all.
 #pragma once
 
+// The kernel headers (this file, align_kernel.cuh, rows_kernel.cuh, myers.cuh, bitpal.cuh) also compile under NVRTC:
+// jit.cu instantiates BitPAl kernels for scoring schemes that were not built into the library (the run-time counterpart
+// of the reference's Java generator).  NVRTC has no host headers, hence the typedefs.
+#ifdef __CUDACC_RTC__
+typedef signed char int8_t;
+typedef unsigned char uint8_t;
+typedef short int16_t;
+typedef unsigned short uint16_t;
+typedef int int32_t;
+typedef unsigned int uint32_t;
+typedef long long int64_t;
+typedef unsigned long long uint64_t;
+typedef unsigned long long uintptr_t;
+#else
 #include <cuda_runtime.h>
 #include <stdint.h>
+#endif
 
 namespace bgsa {
 
@@ -39,6 +54,7 @@ struct PackedSubjects {
 
 __host__ __device__ inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 
+#ifndef __CUDACC_RTC__
 __host__ inline PackedSubjects make_packed_view(void *base, int slen, int64_t count) {
     PackedSubjects v;
     v.count = count;
@@ -61,6 +77,7 @@ __host__ inline int64_t packed_bytes(int slen, int64_t count) {
     return align_up(ntiles * ku * 32 * (int64_t)sizeof(uint4), 256) +
            align_up(ntiles * kn * 32 * (int64_t)sizeof(uint32_t), 256) + align_up(ntiles, 256);
 }
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // integer-pipe primitives

@@ -28,6 +28,7 @@ namespace bgsa {
 __host__ __device__ inline int rows_stage_bytes(int stride) { return (32 * stride + 15 + 15) / 16 * 16; }
 // worst number of lanes whose byte loads fall into the same shared-memory bank (all lanes read the same column i of
 // their own row: address = lane * stride + i)
+#ifndef __CUDACC_RTC__
 __host__ inline int rows_bank_conflict_degree(int stride) {
     int worst = 0;
     for (int sub = 0; sub < 4; sub++) {
@@ -37,6 +38,7 @@ __host__ inline int rows_bank_conflict_degree(int stride) {
     }
     return worst;
 }
+#endif
 
 __host__ __device__ constexpr int byte_code(int b) { return b == 'C' ? 1 : b == 'G' ? 2 : b == 'T' ? 3 : b == 'N' ? 4 : 0; }
 

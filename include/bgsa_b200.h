@@ -167,6 +167,14 @@ int bgsa_align_rows_device(const bgsa_params_t *p, const char *h_queries, int n_
 /* Name of what bgsa_align_rows_device runs for these parameters; *fused = 1 when that is ONE kernel fed with the ASCII rows
  * (no pack launch, no packed buffer), 0 when it is the pack kernel followed by bgsa_align_device's kernel. */
 int bgsa_rows_kernel_name(const bgsa_params_t *p, int query_len, int subject_len, char *buf, int buflen, int *fused);
+/* BitPAl scoring schemes.  The schemes listed at build time (make SCHEMES="2,-3,-5 ...") are template instances inside
+ * the library.  Any other valid (match, mismatch, gap) -- gap < 0, match > mismatch, match >= 0, match - 2 gap <= 63
+ * (non-packed: 24) after the common factor is divided out -- is instantiated on first use by NVRTC from the same kernel
+ * headers (embedded in the library) and cached in $BGSA_JIT_CACHE (default ~/.cache/bgsa_b200): the run-time counterpart
+ * of running the reference's generator for a new scheme (generator/.../Main.java:240-315).  bgsa_jit_precompile does that
+ * compile ahead of time (no GPU needed); BGSA_OK at once for built-in schemes and for the Myers algorithms.  Without
+ * libnvrtc such schemes report BGSA_ERR_UNSUPPORTED. */
+int bgsa_jit_precompile(const bgsa_params_t *p, int query_len, int subject_len);
 /* Number of kernel launches issued by this library since load (bench.py "gpu_launches"). */
 int64_t bgsa_launch_count(void);
 /* Name of the kernel instance bgsa_align_device would use, e.g. "bitpal_packed<2,-3,-5,K=5,L=1>". */

@@ -557,6 +557,64 @@ def test_rows_kernel_eligibility(B):
     assert (B.align_batch(p, q, s) == R.oracle_batch(0, q, s)).all()
 
 
+JIT_SCHEMES = [(0, -1, -1), (4, -6, -10), (5, -3, -4), (1, -1, -2), (3, -2, -4), (2, -1, -1), (1, -2, -3), (6, -1, -7), (10, -15, -25)]
+
+
+@pytest.mark.parametrize("M,I,G", JIT_SCHEMES)
+def test_unlisted_scoring_schemes_instantiated_at_run_time(B, M, I, G, tmp_path_factory, monkeypatch):
+    """Any valid (match, mismatch, gap) runs: schemes outside the compiled list are instantiated by NVRTC from the embedded
+    kernel headers (csrc/jit.cu) -- what the reference does by re-running its generator (Main.java:240-315; the (0,-1,-1)
+    "edit" special case :270-272; the common-factor reduction :213-267, here (4,-6,-10) and (10,-15,-25)).  Packed,
+    non-packed and semi-global, thread-per-subject (rows kernel and packed tiles) and wavefront geometries, against plain
+    DP and the restated BitPAl (oracle)."""
+    monkeypatch.setenv("BGSA_JIT_CACHE", str(tmp_path_factory.getbasetemp() / "jit"))     # shared by the parametrised cases
+    rng = np.random.default_rng(1000 + M * 100 - I * 10 - G)
+    # (query, subject, count, variants): every instance is one NVRTC compile (1-10 s), so the full sweep of geometries runs
+    # for two schemes and the others take the thread-per-subject kernels plus one wavefront instance
+    P, N, S = B.BITPAL_PACKED, B.BITPAL_NONPACKED, B.BITPAL_PACKED_SEMIGLOBAL
+    if (M, I, G) in JIT_SCHEMES[:2]:
+        geos = [(150, 150, 200, (P, N, S)), (60, 90, 70, (P, N, S)), (300, 127, 64, (P,)), (700, 300, 40, (P, S)), (2100, 150, 33, (P,))]
+    else:
+        geos = [(150, 150, 200, (P, N, S)), (700, 300, 40, (P,))]
+    for ql, sl, ns, variants in geos:
+        q = R.random_rows(rng, 2, ql, with_n=0.01)
+        s = R.random_rows(rng, ns, sl, with_n=0.01)
+        m = min(ql, sl)
+        s[: ns // 3, :m] = q[0, :m]
+        s[ns // 3: ns // 2, :m] = R.mutate_rows(rng, q[1, :m], ns // 2 - ns // 3, max(1, m // 12))[:, :m]
+        kw = dict(match=M, mismatch=I, gap=G)
+        dp = R.dp_scores("nw", q, s[:6], M=M, I=I, G=G).astype(np.int16)
+        for algo in (P, N):
+            if algo not in variants:
+                continue
+            p = B.Params.default(algo, **kw)
+            assert B.kernel_name(p, ql, sl).endswith("[NVRTC]")
+            got = B.align_batch(p, q, s)
+            assert (got == R.oracle_batch(R.ALGO_BITPAL_PACKED, q, s, M=M, I=I, G=G)).all(), (algo, M, I, G, ql, sl)
+            assert (got[:, :6] == dp).all(), (algo, M, I, G, ql, sl)
+        if S in variants:
+            p = B.Params.default(S, **kw)
+            got = B.align_batch(p, q, s)
+            assert (got == R.oracle_batch(R.ALGO_BITPAL_SEMI, q, s, M=M, I=I, G=G)).all(), ("semi", M, I, G, ql, sl)
+            assert (got[:, :6] == R.dp_scores("nw_semi", q, s[:6], M=M, I=I, G=G).astype(np.int16)).all()
+    # the device-resident entries take the same route (packed tiles, and the rows kernel on its own)
+    import torch
+    q = R.random_rows(rng, 1, 150); s = R.random_rows(rng, 4097, 150, with_n=0.01)
+    p = B.Params.default(B.BITPAL_PACKED, match=M, mismatch=I, gap=G)
+    d_rows = torch.from_numpy(s.reshape(-1)).cuda()
+    d_res = torch.zeros(4097, dtype=torch.int16, device="cuda")
+    B.align_rows_device(p, q, d_rows.data_ptr(), 150, 4097, d_res.data_ptr(), 4097)
+    torch.cuda.synchronize()
+    exp = R.oracle_batch(R.ALGO_BITPAL_PACKED, q, s, M=M, I=I, G=G)
+    assert (d_res.cpu().numpy().reshape(1, -1) == exp).all()
+    d_packed = torch.empty(B.packed_bytes(150, 4097), dtype=torch.uint8, device="cuda")
+    d_res.zero_()
+    B.pack_subjects_device(p, d_rows.data_ptr(), 150, 4097, d_packed.data_ptr())
+    B.align_device(p, q, d_packed.data_ptr(), 150, 4097, d_res.data_ptr(), 4097)
+    torch.cuda.synchronize()
+    assert (d_res.cpu().numpy().reshape(1, -1) == exp).all()
+
+
 @pytest.mark.parametrize("force", ["1", "0"])
 def test_batch_entry_host_pack_front_end(B, force, monkeypatch):
     """bgsa_align_batch with the subjects encoded by the host threads (BGSA_HOST_PACK=1: csrc/host_pack.cpp, a quarter of

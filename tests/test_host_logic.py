@@ -67,7 +67,9 @@ def test_no_cpu_fallback_and_error_codes():
     assert (p.match, p.mismatch, p.gap, p.threshold, p.myers_sign) == (2, -3, -5, 31, -1)
     assert B.load().bgsa_result_size(B.BANDED_MYERS) == 1 and B.load().bgsa_result_size(B.MYERS_GLOBAL) == 2
     # unsupported requests are rejected before any CUDA call
-    assert not B.supported(B.Params.default(B.BITPAL_PACKED, match=7, mismatch=-1, gap=-3), 100, 100)
+    assert B.supported(B.Params.default(B.BITPAL_PACKED, match=7, mismatch=-1, gap=-3), 100, 100)     # not built in: instantiated at run time
+    assert not B.supported(B.Params.default(B.BITPAL_PACKED, match=2, mismatch=3, gap=-5), 100, 100)  # not a scoring scheme
+    assert not B.supported(B.Params.default(B.BITPAL_PACKED, match=60, mismatch=-1, gap=-30), 100, 100)   # delta range beyond the kernels
     assert not B.supported(B.Params.default(B.BANDED_MYERS, threshold=5), 100, 120)
     assert not B.supported(B.Params.default(B.BANDED_MYERS, threshold=40), 100, 100)
     assert not B.supported(B.Params.default(B.MYERS_GLOBAL), 40000, 100)
@@ -173,6 +175,49 @@ print('ok')
     env = dict(os.environ, BGSA_HOST_THREADS="48")
     res = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
     assert res.returncode == 0 and "ok" in res.stdout, (res.returncode, res.stderr[-2000:])
+
+
+def test_jit_precompile_needs_no_gpu(tmp_path, monkeypatch):
+    """Scoring schemes outside the compiled list are instantiated by NVRTC from the kernel headers embedded in the library
+    (csrc/jit.cu; the run-time counterpart of the reference's generator, Main.java:240-315).  The compile itself needs no
+    GPU: the headers must stay NVRTC-clean, the instance lands in the disk cache, invalid schemes are refused with the
+    reason, and without NVRTC an unlisted scheme is BGSA_ERR_UNSUPPORTED as before."""
+    import bgsa_b200 as B
+    _ensure_built()
+    monkeypatch.setenv("BGSA_JIT_CACHE", str(tmp_path / "jit"))
+    builtin = B.Params.default(B.BITPAL_PACKED)
+    B.jit_precompile(builtin, 150, 150)                                   # built in: nothing to compile
+    assert not (tmp_path / "jit").exists()
+    cases = [(B.BITPAL_PACKED, (0, -1, -1), 150), (B.BITPAL_PACKED, (4, -6, -10), 100), (B.BITPAL_NONPACKED, (1, -1, -2), 150),
+             (B.BITPAL_PACKED_SEMIGLOBAL, (5, -3, -4), 150), (B.BITPAL_PACKED, (1, -1, -2), 2000)]
+    for algo, (M, I, G), ql in cases:
+        p = B.Params.default(algo, match=M, mismatch=I, gap=G)
+        assert B.supported(p, ql, ql)
+        assert B.kernel_name(p, ql, ql).endswith("[NVRTC]")
+        B.jit_precompile(p, ql, ql)
+    files = sorted((tmp_path / "jit").glob("bgsa_*.bin"))
+    assert len(files) == len(cases) and all(f.stat().st_size > 10_000 for f in files)
+    stamp = [f.stat().st_mtime_ns for f in files]
+    for algo, (M, I, G), ql in cases:                                     # second time: from the cache, nothing rewritten
+        B.jit_precompile(B.Params.default(algo, match=M, mismatch=I, gap=G), ql, ql)
+    assert stamp == [f.stat().st_mtime_ns for f in files]
+    for M, I, G in ((2, 3, -5), (2, -3, 5), (-1, -2, -3), (3, 3, -1), (64, -1, -33)):
+        p = B.Params.default(B.BITPAL_PACKED, match=M, mismatch=I, gap=G)
+        assert not B.supported(p, 150, 150)
+        with pytest.raises(B.BgsaError) as ei:
+            B.jit_precompile(p, 150, 150)
+        assert ei.value.code == 2 and "scoring scheme" in str(ei.value)
+    code = """
+import sys
+sys.path.insert(0, %r)
+import bgsa_b200 as B
+p = B.Params.default(B.BITPAL_PACKED, match=4, mismatch=-6, gap=-10)
+assert not B.supported(p, 150, 150)
+assert B.supported(B.Params.default(B.BITPAL_PACKED), 150, 150)
+print('ok')
+""" % str(ROOT)
+    res = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, BGSA_NO_JIT="1"), capture_output=True, text=True, timeout=120)
+    assert res.returncode == 0 and "ok" in res.stdout, res.stderr
 
 
 def test_sass_carry_chains_and_budget():
