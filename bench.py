@@ -93,8 +93,10 @@ def alg_ops_per_cell(algo: int, qlen: int, slen: int) -> float:
     return 16.0 / slen          # banded: 16 per band row, rows = query length, per NOMINAL cell
 
 
-def alg_bytes_per_subject(algo: int, slen: int) -> float:
-    return slen / 4.0 + (1 if algo == 2 else 2)     # 2-bit bases in, one score out
+def alg_bytes_per_subject(algo: int, slen: int, ascii_in: bool) -> float:
+    """HBM bytes the align kernel must move per subject: the one-kernel paths read the ASCII rows (one byte per base plus
+    the row end), the kernels on packed tiles 2 bits per base; one score out."""
+    return (slen + 1.0 if ascii_in else slen / 4.0) + (1 if algo == 2 else 2)
 
 
 def _git_sha() -> str | None:
@@ -381,7 +383,7 @@ def measure(ctx: Ctx, name: str, steps: int, warmup: int, count: int | None, cpu
     ms_per_step = ms_total / steps
     ops_cell = alg_ops_per_cell(wl["algo"], qlen, slen)
     achieved = ops_cell * cells / (align_ms * 1e-3)               # lane-ops/s of the align kernel, per GPU
-    hbm_bytes = alg_bytes_per_subject(wl["algo"], slen) * ns
+    hbm_bytes = alg_bytes_per_subject(wl["algo"], slen, fused) * ns
     hbm_peak = ctx.peaks.get("hbm_gbs", 6650.0)
     prof = ctx.ncu.get(name if name != "C3s" else "C3", {})
     traffic, pipe_ncu = None, None
@@ -390,7 +392,8 @@ def measure(ctx: Ctx, name: str, steps: int, warmup: int, count: int | None, cpu
     if "alu_pipe_pct" in prof:
         pipe_ncu = {"alu_pipe_busy": prof["alu_pipe_pct"] / 100.0, "issue_slots_busy": prof["issue_active_pct"] / 100.0,
                     "fma_pipe_busy": prof["fma_pipe_pct"] / 100.0, "kernel": prof.get("kernel"), "source": prof.get("source"),
-                    "note": "committed ncu --set full capture of the same kernel, not measured in this run"}
+                    "captured_at_git": prof.get("captured_at_git"),
+                    "note": "committed ncu --set full capture of the same kernel (a profiler cannot run inside a timed bench)"}
     sass = ctx.sass.get(wl["sass"], {})
     ops_cell_sass = sass.get("ops_per_cell_sass")
     rec = {

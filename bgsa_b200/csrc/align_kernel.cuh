@@ -11,6 +11,7 @@
 //         a CarryOut stream with bits 0..2 clear.
 //     static constexpr uint32_t kBoundary;            // carry-in bits at the top row (lane 0)
 //     static constexpr int kOpsPerWord;               // rough ALU instructions per word-column (unrolling policy)
+//     static constexpr int kMinBlocksWavefront;       // resident CTAs per SM the L > 1 instances are compiled for
 //     static Partial partial(const State&, int first_bit, int qlen);   // per-lane score pieces
 //     static int final_score(sum, min_prefix, qlen, slen, Params);     // 32-bit score
 //
@@ -51,7 +52,7 @@ __host__ __device__ constexpr int peq_row_stride(int k, int lanes) { return peq_
 #endif
 
 template <class Algo, int L, int CH, int THREADS, int UNROLL>
-__global__ void __launch_bounds__(THREADS, BGSA_MIN_BLOCKS)
+__global__ void __launch_bounds__(THREADS, (L > 1 ? Algo::kMinBlocksWavefront : BGSA_MIN_BLOCKS))
 align_kernel(PackedSubjects ps, const uint32_t *__restrict__ g_peq, int n_queries, int qlen, int16_t *__restrict__ results,
              long long result_stride, typename Algo::Params prm, unsigned long long *__restrict__ counters) {
     constexpr int K = Algo::K;

@@ -74,6 +74,7 @@ struct BitpalPacked {
     static constexpr int A = S::A, B = S::B, NB = S::NB, NH = S::NH;
     static constexpr bool SEMI = MODE == BITPAL_SEMIGLOBAL;
     static constexpr int kOpsPerWord = 65;
+    static constexpr int kMinBlocksWavefront = BGSA_MIN_BLOCKS;
     static constexpr int E0 = SEMI ? -S::G : 0;              // e_{-1}: horizontal delta of the top row, minus G
     using Params = BitpalParams;
     // semi-global only: tmask[j] = the bit of word j that is the last query row (0: not in this word),
@@ -278,6 +279,7 @@ struct BitpalNonPacked {
     static constexpr int K = K_;
     static constexpr int A = S::A, B = S::B, NH = S::NH;
     static constexpr int kOpsPerWord = 185;
+    static constexpr int kMinBlocksWavefront = BGSA_MIN_BLOCKS;
     using Params = BitpalParams;
     struct State { uint32_t d[A][K]; };        // d[v-1][j] = [d == v]
 

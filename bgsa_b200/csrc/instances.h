@@ -6,13 +6,14 @@
 // X(K, L): K 32-bit words per lane, L lanes per subject; serves queries up to 32*K*L bases.
 // Among the instances that fit a query the cheapest is used (api.cu pick(): L * (K * ops per word
 // + per-step wavefront overhead)): wide lanes amortise the carry hand-over, few lanes waste less
-// of the last word.
+// of the last word.  (16, 2) is never the cheapest -- (32, 1) serves the same queries without the hand-over; it exists for
+// the like-for-like measurement of the wavefront against thread-per-subject on C4 (BGSA_FORCE_KL=16,2).
 #pragma once
 
 // Myers global / semi-global
 #define BGSA_MYERS_INSTANCES(X)                                                              \
     X(1, 1) X(2, 1) X(3, 1) X(4, 1) X(5, 1) X(6, 1) X(7, 1) X(8, 1) X(10, 1) X(12, 1) X(16, 1) \
-    X(20, 1) X(24, 1) X(32, 1) X(24, 2) X(32, 2) X(24, 4) X(32, 4) X(20, 8) X(24, 8) X(32, 8)  \
+    X(20, 1) X(24, 1) X(32, 1) X(16, 2) X(24, 2) X(32, 2) X(24, 4) X(32, 4) X(20, 8) X(24, 8) X(32, 8)  \
     X(24, 16) X(32, 16) X(24, 32) X(32, 32)
 
 // BitPAl packed (global and semi-global)

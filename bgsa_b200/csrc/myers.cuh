@@ -29,6 +29,12 @@ template <int K_, int MODE>
 struct MyersAlgo {
     static constexpr int K = K_;
     static constexpr int kOpsPerWord = 10;
+    // Wavefront instances: left alone ptxas takes 173-199 registers (2 CTAs = 2 warps per SM sub-partition, ALU pipe 94 %
+    // busy, profiles/r02_ncu_metrics.csv myers5k); capped for 3 CTAs they need 141-152 without a single spill.
+#ifndef BGSA_MYERS_WF_MINBLOCKS
+#define BGSA_MYERS_WF_MINBLOCKS 3
+#endif
+    static constexpr int kMinBlocksWavefront = BGSA_MYERS_WF_MINBLOCKS;
     using Params = MyersParams;
     struct State { uint32_t pv[K], mv[K]; };
     // carry stream (CarryIn/CarryOut, consumption order): add carry, Ph shift-in, Mh shift-in

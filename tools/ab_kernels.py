@@ -77,4 +77,7 @@ run("C2np", B.BITPAL_NONPACKED, 150, 150, 300_000)
 run("bp111", B.BITPAL_PACKED, 150, 150, 1_000_000, match=1, mismatch=-1, gap=-1)
 run("C2semi", B.BITPAL_PACKED_SEMIGLOBAL, 150, 150, 1_000_000)
 run("C5semi", B.BITPAL_PACKED_SEMIGLOBAL, 5000, 5000, 8192, reps=4)
-run("myers5k", B.MYERS_GLOBAL, 5000, 5000, 16384, reps=4)
+run("myers5k", B.MYERS_GLOBAL, 5000, 5000, 65536, reps=4)
+run("myers2k", B.MYERS_GLOBAL, 2000, 2000, 262144, reps=4)
+run("myers20k", B.MYERS_GLOBAL, 20000, 1000, 131072, reps=4)
+run("C4semi2k", B.MYERS_SEMIGLOBAL, 2000, 1000, 131072, reps=4)

@@ -1,11 +1,12 @@
 """Distils `ncu --page raw --csv` exports (tools/profile_all.sh) into profiles/: one compact CSV of the metrics
 that evidence the design choices (ALU/FMA pipe utilisation, issue rate, DRAM bytes, occupancy, stall reasons)
 and profiles/ncu_summary.json, which bench.py reads for `roofline.traffic`.
-    python tools/ncu_summarize.py gpurun_out/r01prof r01"""
+    python tools/ncu_summarize.py gpurun_out/r02prof r02 <git sha of the captured build>"""
 import csv, json, sys
 from pathlib import Path
 
 src, tag = Path(sys.argv[1]), sys.argv[2]
+git_sha = sys.argv[3] if len(sys.argv) > 3 else None      # commit the captured library was built from
 ROOT = Path(__file__).resolve().parent.parent
 KEEP = [
     "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
@@ -25,7 +26,8 @@ KEEP = [
     "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
     "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio",
 ]
-SUBJECTS = {"C2": 1_000_000, "C3": 10_000_000, "C4": 1_000_000, "C5": 32768, "myers150": 1_000_000}
+SUBJECTS = {"C2": 1_000_000, "C3": 10_000_000, "C3s": 10_000_000, "C4": 1_000_000, "C5": 32768, "myers150": 1_000_000, "C2np": 300_000,
+            "myers5k": 16384, "C4_wavefront_K24_L2": 300_000}
 UNIT = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "ms": 1e-3, "us": 1e-6, "s": 1.0, "ns": 1e-9}
 
 
@@ -51,15 +53,20 @@ for f in sorted(src.glob("full_*.raw.csv")):
             rows.append([tag, wl, kern, m, d[m][0], d[m][1]])
     rd, wr = num(*d["dram__bytes_read.sum"]), num(*d["dram__bytes_write.sum"])
     dur = num(*d["gpu__time_duration.sum"])
-    entry = {"kernel": kname[:140], "subjects_in_capture": SUBJECTS[wl], "dram_bytes_per_launch": rd + wr,
-             "dram_bytes_per_subject": (rd + wr) / SUBJECTS[wl], "duration_s_under_ncu": dur,
+    nsub = SUBJECTS.get(f"{wl}_{kern}", SUBJECTS[wl])
+    entry = {"kernel": kname[:140], "subjects_in_capture": nsub, "dram_bytes_per_launch": rd + wr,
+             "dram_bytes_per_subject": (rd + wr) / nsub, "duration_s_under_ncu": dur,
              "alu_pipe_pct": float(d["sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"][0]),
              "fma_pipe_pct": float(d["sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active"][0]),
              "issue_active_pct": float(d["smsp__issue_active.avg.pct_of_peak_sustained_active"][0]),
              "dram_pct_of_peak": float(d["dram__cycles_active.avg.pct_of_peak_sustained_elapsed"][0]),
              "registers": int(float(d["launch__registers_per_thread"][0])),
-             "source": f"profiles/{tag}_ncu_metrics.csv (ncu --set full --clock-control none, tools/profile_all.sh)"}
-    summary[wl if "pack" not in kern else f"{wl}_pack"] = entry
+             "source": f"profiles/{tag}_ncu_metrics.csv (ncu --set full --clock-control none, tools/profile_all.sh)",
+             "captured_at_git": git_sha}
+    stalls = {m.split("issue_stalled_")[1].split("_per_issue")[0]: float(d[m][0]) for m in KEEP if "issue_stalled" in m and m in d}
+    entry["stalls_per_issue"] = stalls
+    main = kern in ("align_rows_kernel", "banded_kernel", "align_kernel")
+    summary[wl if main else f"{wl}_{kern}"] = entry
 out = ROOT / "profiles" / f"{tag}_ncu_metrics.csv"
 with open(out, "w", newline="") as fh:
     w = csv.writer(fh)

@@ -6,9 +6,9 @@ sys.path.insert(0, str(Path(__file__).resolve().parent.parent)); sys.path.insert
 import numpy as np, torch
 import bgsa_b200 as B, synth
 name = sys.argv[1] if len(sys.argv) > 1 else "C2"
-W = {"C2": ("C2", 3, {}), "C3": ("C3", 2, {"threshold": 5}), "C4": ("C4", 1, {}), "C5": ("C5", 3, {}), "myers150": ("C2", 0, {}), "C2np": ("C2", 4, {})}
+W = {"C2": ("C2", 3, {}), "C3": ("C3", 2, {"threshold": 5}), "C4": ("C4", 1, {}), "C5": ("C5", 3, {}), "myers150": ("C2", 0, {}), "C2np": ("C2", 4, {}), "myers5k": ("C5", 0, {}), "C3s": ("C3s", 2, {"threshold": 5})}
 cfg, algo, kw = W[name]
-count = int(sys.argv[2]) if len(sys.argv) > 2 else {"C2": 1_000_000, "C3": 10_000_000, "C4": 300_000, "C5": 8192, "myers150": 1_000_000, "C2np": 300_000}[name]
+count = int(sys.argv[2]) if len(sys.argv) > 2 else {"C2": 1_000_000, "C3": 10_000_000, "C4": 300_000, "C5": 8192, "myers150": 1_000_000, "C2np": 300_000, "myers5k": 16384, "C3s": 10_000_000}[name]
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
 q, s = synth.make(cfg, count)
 p = B.Params.default(algo, **kw)
