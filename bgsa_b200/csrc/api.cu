@@ -205,6 +205,11 @@ struct Job {
     QueryCache qc;
     cudaEvent_t tab_ready = nullptr;
     cudaEvent_t t0 = nullptr;            // trace origin
+    // link feedback of the hybrid front end: the H2D copies of the last chunks, bracketed by timing events
+    struct LinkItem { cudaEvent_t begin = nullptr, end = nullptr; double bytes = 0.0; bool pending = false; };
+    static constexpr int kLinkItems = 8;
+    LinkItem link[kLinkItems];
+    double link_rate = 0.0;              // H2D bytes/s the hybrid front end measured on its last job (0: not yet)
     std::vector<ChunkTrace> trace;
 };
 // State of the device-resident entry points (bgsa_align_device / bgsa_align_rows_device), ONE PER CALLER STREAM: query
@@ -753,15 +758,65 @@ static int submit_impl(const bgsa_params_t *p, const char *queries, int n_querie
     }
     int li = 0;
     // hybrid bookkeeping (host clock): when the link will have drained what has been queued on it, and the threads' measured rate
-    double link_free = host_now_s(), pack_rate = HostPool::instance().threads() * 4.0e9;
+    // hybrid bookkeeping, all MEASURED: the threads' pack rate, and the link's state read back from the lanes' copy events --
+    // bytes still queued on the link and the rate at which the finished copies really moved (with several ranks on one
+    // host the link delivers a fraction of its nominal rate: 184 GB/s for 8 GPUs together against 55 for one alone)
+    double pack_rate = HostPool::instance().threads() * 4.0e9, link_rate = job.link_rate > 0 ? job.link_rate : kPcieBytesPerS;
+    // A copy's own duration = from the later of (its begin event, the end of the copy queued before it) to its end: the
+    // lanes' copies share one engine, so a copy queued behind another would otherwise look slow.
+    auto link_backlog_s = [&]() {
+        double queued = 0.0;
+        for (int i = 0; i < Job::kLinkItems; i++) {
+            Job::LinkItem &x = job.link[i];
+            if (!x.pending) continue;
+            if (cudaEventQuery(x.end) == cudaSuccess) {
+                float own = 0.f, after_prev = 0.f;
+                const Job::LinkItem &prev = job.link[(i + Job::kLinkItems - 1) % Job::kLinkItems];
+                if (x.bytes >= (1 << 20) && cudaEventElapsedTime(&own, x.begin, x.end) == cudaSuccess && own > 0.f) {
+                    if (prev.end && !prev.pending && cudaEventElapsedTime(&after_prev, prev.end, x.end) == cudaSuccess && after_prev > 0.f &&
+                        after_prev < own)
+                        own = after_prev;
+                    link_rate = 0.5 * link_rate + 0.5 * x.bytes / (1e-3 * own);
+                }
+                cudaGetLastError();
+                x.pending = false;
+            } else {
+                cudaGetLastError();                       // cudaErrorNotReady is not an error
+                queued += x.bytes;
+            }
+        }
+        return queued / link_rate;
+    };
+    int link_slot = 0;
+    double ascii_credit = 1.0 - 1e-9;
+    auto link_begin = [&](cudaStream_t st) -> int {
+        Job::LinkItem &x = job.link[link_slot];
+        if (!x.begin && (cudaEventCreate(&x.begin) != cudaSuccess || cudaEventCreate(&x.end) != cudaSuccess)) return BGSA_ERR_CUDA;
+        x.pending = false;
+        return cudaEventRecord(x.begin, st) == cudaSuccess ? BGSA_OK : BGSA_ERR_CUDA;
+    };
+    auto link_end = [&](cudaStream_t st, double bytes) -> int {
+        Job::LinkItem &x = job.link[link_slot];
+        link_slot = (link_slot + 1) % Job::kLinkItems;
+        x.bytes = bytes; x.pending = true;
+        return cudaEventRecord(x.end, st) == cudaSuccess ? BGSA_OK : BGSA_ERR_CUDA;
+    };
     for (int64_t off = 0, step = first_chunk; off < count; off += step, step = chunk, li = (li + 1) % kLanesPerJob) {
         const int64_t n = count - off < step ? count - off : step;
         Lane &l = job.lane[li];
         bool host_pack = hp_mode == HP_ALWAYS;
         if (hp_mode == HP_HYBRID) {
             // would the link still be busy by the time the threads had encoded this chunk?  then encode; else feed the link
-            const double backlog = link_free - host_now_s();
-            host_pack = backlog > 0.5 * (double)n * (slen + 1) / pack_rate;
+            // Share of the chunks that should cross the link as ASCII so that link and threads finish together:
+            //   x Tl + (1-x) Tl/4 = (1-x) Tp   (Tl, Tp: link / pack time of a chunk)   =>   x = (Tp - Tl/4) / (Tp + 3 Tl/4),
+            // dealt out by error diffusion (the first chunk goes over the link: the threads start on the second at once).
+            (void)link_backlog_s();                               // (reads the finished copies: updates link_rate)
+            const double tp = 1.0 / pack_rate, tl = 1.0 / link_rate;
+            double x = (tp - 0.25 * tl) / (tp + 0.75 * tl);
+            x = x < 0.0 ? 0.0 : (x > 1.0 ? 1.0 : x);
+            ascii_credit += x;
+            host_pack = ascii_credit < 1.0;
+            if (!host_pack) ascii_credit -= 1.0;
         }
         const bool fused = can_fuse && !host_pack;
         ChunkTrace tr{off, n, li, {nullptr, nullptr, nullptr, nullptr}, host_pack ? 1 : 0};
@@ -784,23 +839,25 @@ static int submit_impl(const bgsa_params_t *p, const char *queries, int n_querie
                                                slen, n, l.h_packed.p);
             const double t_pack1 = host_now_s();
             if (t_pack1 > t_pack0) pack_rate = 0.5 * pack_rate + 0.5 * (double)row_bytes / (t_pack1 - t_pack0);
-            link_free = std::max(link_free, t_pack1) + (double)row_bytes / 4.0 / kPcieBytesPerS;
             const PackedSubjects hv = make_packed_view(l.h_packed.p, slen, n);
             const char *hb = static_cast<const char *>(l.h_packed.p);
             char *db = static_cast<char *>(l.d_packed.p);
             const size_t codes_bytes = (size_t)hv.ntiles * hv.ku * 32 * sizeof(uint4);
             const size_t nm_off = (size_t)(reinterpret_cast<const char *>(hv.nmask) - hb), fl_off = (size_t)(reinterpret_cast<const char *>(hv.tile_has_n) - hb);
+            if (hp_mode == HP_HYBRID && link_begin(l.stream)) return fail(BGSA_ERR_CUDA, "event record failed");
             CUDA_TRY(cudaMemcpyAsync(db, hb, codes_bytes, cudaMemcpyHostToDevice, l.stream));
             CUDA_TRY(cudaMemcpyAsync(db + fl_off, hb + fl_off, (size_t)hv.ntiles, cudaMemcpyHostToDevice, l.stream));
             if (any_n) CUDA_TRY(cudaMemcpyAsync(db + nm_off, hb + nm_off, (size_t)hv.ntiles * hv.kn * 32 * sizeof(uint32_t), cudaMemcpyHostToDevice, l.stream));
             if (!l.staged) CUDA_TRY(cudaEventCreateWithFlags(&l.staged, cudaEventDisableTiming));
             CUDA_TRY(cudaEventRecord(l.staged, l.stream));
             l.staged_pending = true;
+            if (hp_mode == HP_HYBRID && link_end(l.stream, (double)codes_bytes)) return fail(BGSA_ERR_CUDA, "event record failed");
         } else {
             // host -> device: the ASCII rows exactly as file.c:44-115 left them
+            if (hp_mode == HP_HYBRID && link_begin(l.stream)) return fail(BGSA_ERR_CUDA, "event record failed");
             CUDA_TRY(cudaMemcpyAsync(l.d_rows.p, subjects->content + (size_t)(first + off) * (slen + 1), row_bytes,
                                      cudaMemcpyHostToDevice, l.stream));
-            link_free = std::max(link_free, host_now_s()) + (double)row_bytes / kPcieBytesPerS;
+            if (hp_mode == HP_HYBRID && link_end(l.stream, (double)row_bytes)) return fail(BGSA_ERR_CUDA, "event record failed");
         }
         mark(0);
         if (!fused && !host_pack) {
@@ -820,6 +877,9 @@ static int submit_impl(const bgsa_params_t *p, const char *queries, int n_querie
         mark(3);
         if (kTrace) job.trace.push_back(tr);
     }
+    job.link_rate = link_rate;                          // the next job on this slot starts from what this one measured
+    if (kTrace && hp_mode == HP_HYBRID)
+        fprintf(stderr, "[bgsa trace] hybrid front end: link %.1f GB/s, host pack %.1f GB/s (measured)\n", link_rate / 1e9, pack_rate / 1e9);
     return BGSA_OK;
 }
 
