@@ -23,7 +23,7 @@ __all__ = [
     "MYERS_GLOBAL", "MYERS_SEMIGLOBAL", "BANDED_MYERS", "BITPAL_PACKED", "BITPAL_NONPACKED", "BITPAL_PACKED_SEMIGLOBAL",
     "BgsaError", "Params", "SeqT", "load", "lib_path", "align_batch", "result_dtype", "to_codes",
     "align_batch_submit", "align_batch_wait", "init_devices",
-    "packed_bytes", "pack_subjects_device", "pack_subjects_host", "host_pack_info", "align_device", "align_rows_device", "int_peak", "bind_thread_to_device", "launch_count", "kernel_name", "rows_kernel_name", "supported", "jit_precompile",
+    "packed_bytes", "pack_subjects_device", "pack_subjects_host", "host_pack_info", "align_device", "align_rows_device", "int_peak", "bind_thread_to_device", "launch_count", "kernel_name", "rows_kernel_name", "supported", "jit_precompile", "batch_front_end",
 ]
 
 MYERS_GLOBAL, MYERS_SEMIGLOBAL, BANDED_MYERS, BITPAL_PACKED, BITPAL_NONPACKED, BITPAL_PACKED_SEMIGLOBAL = range(6)
@@ -98,6 +98,7 @@ def load():
         "bgsa_kernel_name": (i32, [PP, i32, i32, C.c_char_p, i32]),
         "bgsa_rows_kernel_name": (i32, [PP, i32, i32, C.c_char_p, i32, C.POINTER(i32)]),
         "bgsa_jit_precompile": (i32, [PP, i32, i32]),
+        "bgsa_batch_front_end": (i32, [i32, i32, C.POINTER(C.c_double)]),
         "bgsa_int_peak": (i32, [i32, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
         "bgsa_align_peq_chunk": (i32, [PP, vp, i32, vp, i32, i32, i32, i32, i32, i64, vp, i32]),
     }
@@ -112,7 +113,7 @@ EXPORTED_SYMBOLS = [
     "bgsa_version", "bgsa_last_error", "bgsa_device_count", "bgsa_init_devices", "bgsa_params_default", "bgsa_result_size", "bgsa_supported",
     "bgsa_align_batch", "bgsa_align_batch_submit", "bgsa_align_batch_wait", "bgsa_malloc_host", "bgsa_free_host",
     "bgsa_host_register", "bgsa_host_unregister", "bgsa_bind_thread_to_device",
-    "bgsa_packed_bytes", "bgsa_pack_subjects_device", "bgsa_pack_subjects_host", "bgsa_host_pack_info", "bgsa_align_device", "bgsa_align_rows_device", "bgsa_launch_count", "bgsa_kernel_name", "bgsa_rows_kernel_name", "bgsa_jit_precompile",
+    "bgsa_packed_bytes", "bgsa_pack_subjects_device", "bgsa_pack_subjects_host", "bgsa_host_pack_info", "bgsa_align_device", "bgsa_align_rows_device", "bgsa_launch_count", "bgsa_kernel_name", "bgsa_rows_kernel_name", "bgsa_jit_precompile", "bgsa_batch_front_end",
     "bgsa_int_peak", "bgsa_align_peq_chunk",
 ]
 
@@ -159,6 +160,13 @@ def rows_kernel_name(params: Params, query_len: int, subject_len: int):
 def jit_precompile(params: Params, query_len: int, subject_len: int) -> None:
     """Compiles (NVRTC) and caches the kernels of a scoring scheme that is not built into the library; needs no GPU."""
     _check(load().bgsa_jit_precompile(C.byref(params), query_len, subject_len))
+
+
+def batch_front_end(device: int = 0, slot: int = 0) -> float:
+    """Share of host-packed chunks of the last batch job on (device, slot): 0 = all ASCII over the link, 1 = all packed on the host."""
+    v = C.c_double(0.0)
+    _check(load().bgsa_batch_front_end(device, slot, C.byref(v)))
+    return v.value
 
 
 def launch_count() -> int:

@@ -205,11 +205,27 @@ struct Job {
     QueryCache qc;
     cudaEvent_t tab_ready = nullptr;
     cudaEvent_t t0 = nullptr;            // trace origin
+    // Front-end tuner (pinned subjects): the share of the chunks the host threads pack, searched job by job on the
+    // measured throughput of the jobs themselves (submit_impl "front end" comment)
+    struct Tuner {
+        std::vector<char> key;          // workload shape the state belongs to
+        double p = 0.0;                 // current best share of host-packed chunks
+        double r_best = 0.0;            // rows bytes/s measured at p
+        double step = 0.25;
+        int dir = -1, rejected = 0, hold = 0, hold_len = 4;
+        bool trial = false;             // the job in flight runs at p_trial, not p
+        double p_trial = 0.0;
+        double p_used = 0.0, bytes = 0.0;
+        bool armed = false;             // the job in flight is being timed
+    } tuner;
+    cudaEvent_t ev_begin = nullptr, ev_lane_end[kLanesPerJob] = {};
+    bool lane_used[kLanesPerJob] = {};
     // link feedback of the hybrid front end: the H2D copies of the last chunks, bracketed by timing events
     struct LinkItem { cudaEvent_t begin = nullptr, end = nullptr; double bytes = 0.0; bool pending = false; };
     static constexpr int kLinkItems = 8;
     LinkItem link[kLinkItems];
     double link_rate = 0.0;              // H2D bytes/s the hybrid front end measured on its last job (0: not yet)
+    double last_share = 0.0;             // share of host-packed chunks of the last job (bgsa_batch_front_end)
     std::vector<ChunkTrace> trace;
 };
 // State of the device-resident entry points (bgsa_align_device / bgsa_align_rows_device), ONE PER CALLER STREAM: query
@@ -652,7 +668,10 @@ int bgsa_align_rows_device(const bgsa_params_t *p, const char *h_queries, int n_
 // BGSA_HOST_PACK=0 / 1 forces never / always; =2 forces hybrid.
 enum HostPackMode { HP_NEVER = 0, HP_ALWAYS = 1, HP_HYBRID = 2 };
 constexpr double kPcieBytesPerS = 52e9;     // measured H2D rate of pinned rows on this platform (55 GB/s peak)
-static HostPackMode decide_host_pack(const Plan &plan, int nq, int qlen, int slen, int64_t count, const void *rows) {
+// *tunable: pinned subjects, nothing forced, and a batch whose input path matters -- the model's answer is then only the
+// starting point of the per-job search (Job::Tuner).
+static HostPackMode decide_host_pack(const Plan &plan, int nq, int qlen, int slen, int64_t count, const void *rows, bool *tunable) {
+    *tunable = false;
     if (const char *env = getenv("BGSA_HOST_PACK")) {
         if (env[0] == '0') return HP_NEVER;
         if (env[0] == '1') return HP_ALWAYS;
@@ -678,6 +697,7 @@ static HostPackMode decide_host_pack(const Plan &plan, int nq, int qlen, int sle
     if (!pinned) return std::max(t_pack, t_kernel) < 0.9 * std::max(bytes / 9e9, t_kernel) ? HP_ALWAYS : HP_NEVER;
     if (t_kernel > 2.0 * t_link) return HP_NEVER;                                 // the link hides behind the kernel with room to spare: leave the host
                                                                                   // cores alone and keep the submit call asynchronous (C5: 375 ms of kernel per 12 ms of copy)
+    *tunable = getenv("BGSA_HOST_PACK_NO_TUNING") == nullptr;
     if (t_pack <= 0.9 * t_kernel) return HP_ALWAYS;                               // the threads stay ahead of the kernel: the link is nearly free
     if (t_kernel > 1.15 * t_link) return HP_NEVER;                                // they cannot, and the link hides behind the kernel anyway
     return t_pack < 4.0 * t_link ? HP_HYBRID : HP_NEVER;                          // threads too few to matter: leave them alone
@@ -733,7 +753,51 @@ static int submit_impl(const bgsa_params_t *p, const char *queries, int n_querie
     // same number of rounds.  Small chunks let the kernels follow the H2D stream closely (only the first chunk's
     // copy and the last chunk's kernel are exposed): aim at ~16 chunks, never below one quantum or 4 MB of rows.
     // banded Myers on short rows: one fused kernel per chunk (ASCII tile -> shared-memory strip -> band), no pack launch
-    const HostPackMode hp_mode = decide_host_pack(plan, n_queries, query_len, slen, count, subjects->content + (size_t)first * (slen + 1));
+    // Front end.  The static model (decide_host_pack) knows the nominal link and pack rates of ONE rank on an idle host; with
+    // several ranks on a host the link delivers a fraction of that and the pack threads compete with the DMA engines for
+    // the host's memory bandwidth (8 GPUs on a 32-core host: any host packing LOSES 15 %; 4 GPUs behind one PCIe switch:
+    // it GAINS 20 %; profiles/r02_e2e_multi_rank.log).  For pinned subjects the model therefore only seeds a search: every
+    // job is timed on the device, and the share p of host-packed chunks moves by +-step whenever a trial job beats the
+    // incumbent by 3 % (or ties it with less host work); two failed trials halve the step and double the pause before
+    // the next probe.  The state belongs to the (device, slot) and to the workload shape.
+    bool tunable = false;
+    HostPackMode hp_mode = decide_host_pack(plan, n_queries, query_len, slen, count, subjects->content + (size_t)first * (slen + 1), &tunable);
+    double share = hp_mode == HP_ALWAYS ? 1.0 : (hp_mode == HP_NEVER ? 0.0 : -1.0);    // -1: live model of the measured rates (BGSA_HOST_PACK=2)
+    Job::Tuner &tn = job.tuner;
+    tn.armed = false;
+    if (tunable) {
+        const long long shape[6] = {plan.algo, plan.kl.K, plan.kl.L, slen, n_queries, (long long)(count >> 12)};
+        std::vector<char> key(sizeof(shape));
+        memcpy(key.data(), shape, sizeof(shape));
+        if (key != tn.key) {
+            tn = Job::Tuner();
+            tn.key = key;
+            if (hp_mode == HP_HYBRID) {
+                const double tp = 1.0 / (HostPool::instance().threads() * 4.4e9), tl = 1.0 / kPcieBytesPerS;
+                tn.p = 1.0 - (tp - 0.25 * tl) / (tp + 0.75 * tl);
+            } else {
+                tn.p = share;
+            }
+            share = tn.p;
+        } else {
+            auto clamp01 = [](double v) { return v < 0.0 ? 0.0 : (v > 1.0 ? 1.0 : v); };
+            if (tn.hold > 0) {
+                tn.hold--;
+                share = tn.p;
+            } else {
+                double c = clamp01(tn.p + tn.dir * tn.step);
+                if (c == tn.p) { tn.dir = -tn.dir; c = clamp01(tn.p + tn.dir * tn.step); }
+                tn.trial = c != tn.p;
+                tn.p_trial = c;
+                share = c;
+            }
+        }
+        tn.p_used = share;
+        tn.bytes = (double)count * (slen + 1);
+        tn.armed = true;
+        hp_mode = share >= 1.0 ? HP_ALWAYS : (share <= 0.0 ? HP_NEVER : HP_HYBRID);
+    }
+    const bool live_model = hp_mode == HP_HYBRID && share < 0.0;
     const bool can_fuse = rows_path_fused(plan, slen);                                     // chunks that arrive as ASCII
     long long quantum = 0;
     rc = run_align(plan, ctx->sm_count, d_tab, nullptr, n_queries, query_len, nullptr, slen, 0, nullptr, 0, nullptr, &quantum,
@@ -757,6 +821,14 @@ static int submit_impl(const bgsa_params_t *p, const char *queries, int n_querie
         CUDA_TRY(cudaEventRecord(job.t0, job.lane[0].stream));
     }
     int li = 0;
+    if (tn.armed) {
+        if (!job.ev_begin) {
+            CUDA_TRY(cudaEventCreate(&job.ev_begin));
+            for (cudaEvent_t &e : job.ev_lane_end) CUDA_TRY(cudaEventCreate(&e));
+        }
+        for (bool &u : job.lane_used) u = false;
+        CUDA_TRY(cudaEventRecord(job.ev_begin, job.lane[0].stream));
+    }
     // hybrid bookkeeping (host clock): when the link will have drained what has been queued on it, and the threads' measured rate
     // hybrid bookkeeping, all MEASURED: the threads' pack rate, and the link's state read back from the lanes' copy events --
     // bytes still queued on the link and the rate at which the finished copies really moved (with several ranks on one
@@ -806,13 +878,16 @@ static int submit_impl(const bgsa_params_t *p, const char *queries, int n_querie
         Lane &l = job.lane[li];
         bool host_pack = hp_mode == HP_ALWAYS;
         if (hp_mode == HP_HYBRID) {
-            // would the link still be busy by the time the threads had encoded this chunk?  then encode; else feed the link
-            // Share of the chunks that should cross the link as ASCII so that link and threads finish together:
-            //   x Tl + (1-x) Tl/4 = (1-x) Tp   (Tl, Tp: link / pack time of a chunk)   =>   x = (Tp - Tl/4) / (Tp + 3 Tl/4),
-            // dealt out by error diffusion (the first chunk goes over the link: the threads start on the second at once).
-            (void)link_backlog_s();                               // (reads the finished copies: updates link_rate)
-            const double tp = 1.0 / pack_rate, tl = 1.0 / link_rate;
-            double x = (tp - 0.25 * tl) / (tp + 0.75 * tl);
+            // Share x of the chunks that cross the link as ASCII, dealt out by error diffusion (the first chunk goes over the
+            // link: the threads start on the second at once).  Tuned: x = 1 - share.  Live model (BGSA_HOST_PACK=2): link
+            // and threads finish together when  x Tl + (1-x) Tl/4 = (1-x) Tp  (Tl, Tp: measured link / pack time of a
+            // chunk)  =>  x = (Tp - Tl/4) / (Tp + 3 Tl/4).
+            double x = 1.0 - share;
+            if (live_model) {
+                (void)link_backlog_s();                           // (reads the finished copies: updates link_rate)
+                const double tp = 1.0 / pack_rate, tl = 1.0 / link_rate;
+                x = (tp - 0.25 * tl) / (tp + 0.75 * tl);
+            }
             x = x < 0.0 ? 0.0 : (x > 1.0 ? 1.0 : x);
             ascii_credit += x;
             host_pack = ascii_credit < 1.0;
@@ -844,20 +919,20 @@ static int submit_impl(const bgsa_params_t *p, const char *queries, int n_querie
             char *db = static_cast<char *>(l.d_packed.p);
             const size_t codes_bytes = (size_t)hv.ntiles * hv.ku * 32 * sizeof(uint4);
             const size_t nm_off = (size_t)(reinterpret_cast<const char *>(hv.nmask) - hb), fl_off = (size_t)(reinterpret_cast<const char *>(hv.tile_has_n) - hb);
-            if (hp_mode == HP_HYBRID && link_begin(l.stream)) return fail(BGSA_ERR_CUDA, "event record failed");
+            if (live_model && link_begin(l.stream)) return fail(BGSA_ERR_CUDA, "event record failed");
             CUDA_TRY(cudaMemcpyAsync(db, hb, codes_bytes, cudaMemcpyHostToDevice, l.stream));
             CUDA_TRY(cudaMemcpyAsync(db + fl_off, hb + fl_off, (size_t)hv.ntiles, cudaMemcpyHostToDevice, l.stream));
             if (any_n) CUDA_TRY(cudaMemcpyAsync(db + nm_off, hb + nm_off, (size_t)hv.ntiles * hv.kn * 32 * sizeof(uint32_t), cudaMemcpyHostToDevice, l.stream));
             if (!l.staged) CUDA_TRY(cudaEventCreateWithFlags(&l.staged, cudaEventDisableTiming));
             CUDA_TRY(cudaEventRecord(l.staged, l.stream));
             l.staged_pending = true;
-            if (hp_mode == HP_HYBRID && link_end(l.stream, (double)codes_bytes)) return fail(BGSA_ERR_CUDA, "event record failed");
+            if (live_model && link_end(l.stream, (double)codes_bytes)) return fail(BGSA_ERR_CUDA, "event record failed");
         } else {
             // host -> device: the ASCII rows exactly as file.c:44-115 left them
-            if (hp_mode == HP_HYBRID && link_begin(l.stream)) return fail(BGSA_ERR_CUDA, "event record failed");
+            if (live_model && link_begin(l.stream)) return fail(BGSA_ERR_CUDA, "event record failed");
             CUDA_TRY(cudaMemcpyAsync(l.d_rows.p, subjects->content + (size_t)(first + off) * (slen + 1), row_bytes,
                                      cudaMemcpyHostToDevice, l.stream));
-            if (hp_mode == HP_HYBRID && link_end(l.stream, (double)row_bytes)) return fail(BGSA_ERR_CUDA, "event record failed");
+            if (live_model && link_end(l.stream, (double)row_bytes)) return fail(BGSA_ERR_CUDA, "event record failed");
         }
         mark(0);
         if (!fused && !host_pack) {
@@ -875,11 +950,14 @@ static int submit_impl(const bgsa_params_t *p, const char *queries, int n_querie
         CUDA_TRY(cudaMemcpy2DAsync(static_cast<char *>(results) + esize * (size_t)off, esize * (size_t)result_stride, l.d_results.p,
                                    esize * (size_t)n, esize * (size_t)n, (size_t)n_queries, cudaMemcpyDeviceToHost, l.stream));
         mark(3);
+        if (tn.armed) { CUDA_TRY(cudaEventRecord(job.ev_lane_end[li], l.stream)); job.lane_used[li] = true; }
         if (kTrace) job.trace.push_back(tr);
     }
     job.link_rate = link_rate;                          // the next job on this slot starts from what this one measured
-    if (kTrace && hp_mode == HP_HYBRID)
-        fprintf(stderr, "[bgsa trace] hybrid front end: link %.1f GB/s, host pack %.1f GB/s (measured)\n", link_rate / 1e9, pack_rate / 1e9);
+    job.last_share = hp_mode == HP_ALWAYS ? 1.0 : (hp_mode == HP_NEVER ? 0.0 : (share >= 0.0 ? share : -1.0));
+    if (kTrace && (hp_mode == HP_HYBRID || tunable))
+        fprintf(stderr, "[bgsa trace] front end: share of host-packed chunks %.3f%s, link %.1f GB/s, host pack %.1f GB/s (measured)\n",
+                share, live_model ? " (live model)" : (tn.armed && tn.trial ? " (trial)" : ""), link_rate / 1e9, pack_rate / 1e9);
     return BGSA_OK;
 }
 
@@ -905,6 +983,37 @@ int bgsa_align_batch_wait(int device, int slot) {
     if (rc) return rc;
     Job &job = ctx->job[slot];
     for (Lane &l : job.lane) CUDA_TRY(cudaStreamSynchronize(l.stream));
+    Job::Tuner &tn = job.tuner;
+    if (tn.armed) {                                             // the finished job's verdict (front-end tuner, submit_impl)
+        tn.armed = false;
+        float ms = 0.f, worst = 0.f;
+        for (int i = 0; i < kLanesPerJob; i++)
+            if (job.lane_used[i] && cudaEventElapsedTime(&ms, job.ev_begin, job.ev_lane_end[i]) == cudaSuccess && ms > worst) worst = ms;
+        if (worst > 0.f) {
+            const double r = tn.bytes / (1e-3 * worst);
+            if (tn.trial) {
+                tn.trial = false;
+                const bool less_host_work = tn.p_trial < tn.p;
+                if (r > tn.r_best * 1.03 || (less_host_work && r >= tn.r_best)) {
+                    tn.p = tn.p_trial; tn.r_best = r; tn.rejected = 0;          // accepted: keep walking this way
+                } else {
+                    const bool at_edge = tn.p <= 0.0 || tn.p >= 1.0;
+                    tn.dir = -tn.dir;
+                    tn.rejected += at_edge ? 2 : 1;
+                    if (tn.rejected >= 2) {                                     // both neighbours are worse: settle for a while
+                        tn.rejected = 0;
+                        if (tn.step > 0.0625) tn.step *= 0.5;
+                        tn.hold = tn.hold_len;
+                        if (tn.hold_len < 64) tn.hold_len *= 2;
+                    }
+                }
+            } else {
+                tn.r_best = tn.r_best > 0.0 ? 0.5 * tn.r_best + 0.5 * r : r;
+            }
+        } else {
+            cudaGetLastError();
+        }
+    }
     if (!job.trace.empty()) {
         fprintf(stderr, "[bgsa trace] device %d slot %d: chunk(first,count,lane)  h2d_done pack_done align_done d2h_done [ms since submit]\n",
                 device, slot);
@@ -918,6 +1027,15 @@ int bgsa_align_batch_wait(int device, int slot) {
         }
         job.trace.clear();
     }
+    return BGSA_OK;
+}
+
+int bgsa_batch_front_end(int device, int slot, double *host_pack_share) {
+    if (slot < 0 || slot > 1 || !host_pack_share) return fail(BGSA_ERR_ARG, "bgsa_batch_front_end: bad argument");
+    DeviceCtx *ctx = nullptr;
+    int rc = get_ctx(device, &ctx);
+    if (rc) return rc;
+    *host_pack_share = ctx->job[slot].last_share;
     return BGSA_OK;
 }
 

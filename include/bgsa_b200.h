@@ -164,6 +164,11 @@ int bgsa_align_device(const bgsa_params_t *p, const char *h_queries, int n_queri
 int bgsa_align_rows_device(const bgsa_params_t *p, const char *h_queries, int n_queries, int query_len,
                            const void *d_rows, int subject_len, int64_t count,
                            void *d_results, int64_t result_stride, int device, void *stream);
+/* The front end of the last bgsa_align_batch[_submit] job on (device, slot): the share of its chunks that the host threads
+ * packed (0 = every chunk crossed the link as ASCII, 1 = every chunk was packed on the host; -1 = decided chunk by chunk
+ * from the measured rates, BGSA_HOST_PACK=2).  For pinned subjects the share is tuned job by job on the measured
+ * throughput (BGSA_HOST_PACK_NO_TUNING=1 keeps the static model's choice; BGSA_HOST_PACK=0/1 forces it). */
+int bgsa_batch_front_end(int device, int slot, double *host_pack_share);
 /* Name of what bgsa_align_rows_device runs for these parameters; *fused = 1 when that is ONE kernel fed with the ASCII rows
  * (no pack launch, no packed buffer), 0 when it is the pack kernel followed by bgsa_align_device's kernel. */
 int bgsa_rows_kernel_name(const bgsa_params_t *p, int query_len, int subject_len, char *buf, int buflen, int *fused);
