@@ -19,7 +19,9 @@ Per workload:
              CUDA events, max over ranks; N > 1: every rank owns its own shard of equal size (weak).  Where the one-kernel
              path runs, "two_kernel_path" reports pack + align on packed tiles beside it.
   e2e        the same metric through the reference-facing C-ABI call bgsa_align_batch with PINNED HOST buffers:
-             H2D of the rows and D2H of the scores are inside the timed region every step.
+             H2D of the rows and D2H of the scores are inside the timed region every step.  The library's front end may
+             let the host threads 2-bit-pack a share of the chunks instead of shipping them as ASCII (tuned job by job on
+             measured throughput; the share of the last step is reported); h2d_bytes_per_step counts the ASCII size.
   roofline   the align kernel against the INT32 ALU-pipe roofline.  frac = SURVEY.md section 8d's MODEL instruction
              count / measured duration / peak (can exceed 1 where the kernel needs fewer instructions than the model);
              frac_sass = the same with the ALU-pipe instructions the kernel REALLY executes per cell, counted from
@@ -354,6 +356,7 @@ def measure(ctx: Ctx, name: str, steps: int, warmup: int, count: int | None, cpu
         step_e2e()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    front_end_share = B.batch_front_end(dev, 0)
     crc_all = zlib.crc32(out_pinned.tobytes())
 
     # ---- the checker: the reference on a sample of THIS rank's shard (all ranks); timed on rank 0 at N = 1
@@ -403,7 +406,8 @@ def measure(ctx: Ctx, name: str, steps: int, warmup: int, count: int | None, cpu
         "value_align_kernel_only": cells * world / (align_ms * 1e-3) / 1e9,
         "e2e": {"value": cells * world / (e2e_s / steps) / 1e9, "unit": "GCUPS", "h2d_bytes_per_step": int(ns * (slen + 1)),
                 "d2h_bytes_per_step": int(ns * esize), "ms_per_step": 1e3 * e2e_s / steps,
-                "api": "bgsa_align_batch (pinned host rows in, host scores out)"},
+                "api": "bgsa_align_batch (pinned host rows in, host scores out)",
+                "host_packed_share_of_chunks": front_end_share},
         "gpu_launches": int(launches),
         "roofline": {"bound": "int_alu", "achieved": achieved / 1e12, "peak": ctx.int_peak / 1e12, "unit": "Tlane-op/s",
                      "frac": achieved / ctx.int_peak, "traffic": traffic, "pipe_utilisation_ncu": pipe_ncu,
@@ -610,6 +614,8 @@ def main():
         "host": {"numa_node_of_rank0": ctx.numa_node, "cores": ctx.host_cores},
         "git": _git_sha(),
     }
+    if "two_kernel_path" in head:
+        line["two_kernel_path"] = head["two_kernel_path"]
     if "cpu_baseline" in head:
         line["cpu_baseline"] = head["cpu_baseline"]
     line["parity"] = head["parity"]

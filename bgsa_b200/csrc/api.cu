@@ -702,6 +702,16 @@ static HostPackMode decide_host_pack(const Plan &plan, int nq, int qlen, int sle
     if (t_kernel > 1.15 * t_link) return HP_NEVER;                                // they cannot, and the link hides behind the kernel anyway
     return t_pack < 4.0 * t_link ? HP_HYBRID : HP_NEVER;                          // threads too few to matter: leave them alone
 }
+// Ranks (processes or devices of this process) that pull subjects through this host at the same time: torchrun's
+// LOCAL_WORLD_SIZE / BGSA_HOST_GPUS, or the device contexts this process has brought up.
+static int ranks_sharing_host() {
+    int n = 1;
+    if (const char *g = getenv("BGSA_HOST_GPUS")) n = atoi(g);
+    else if (const char *w = getenv("LOCAL_WORLD_SIZE")) n = atoi(w);
+    int ready = 0;
+    for (int d = 0; d < kMaxDevices; d++) ready += g_ctx[d].ready ? 1 : 0;
+    return std::max(std::max(n, ready), 1);
+}
 static double host_now_s() {
     timespec ts;
     clock_gettime(CLOCK_MONOTONIC, &ts);
@@ -756,12 +766,13 @@ static int submit_impl(const bgsa_params_t *p, const char *queries, int n_querie
     // Front end.  The static model (decide_host_pack) knows the nominal link and pack rates of ONE rank on an idle host; with
     // several ranks on a host the link delivers a fraction of that and the pack threads compete with the DMA engines for
     // the host's memory bandwidth (8 GPUs on a 32-core host: any host packing LOSES 15 %; 4 GPUs behind one PCIe switch:
-    // it GAINS 20 %; profiles/r02_e2e_multi_rank.log).  For pinned subjects the model therefore only seeds a search: every
+    // it GAINS 20 %; profiles/r02_e2e_multi_rank.log).  With several ranks and pinned subjects the model therefore only seeds a search: every
     // job is timed on the device, and the share p of host-packed chunks moves by +-step whenever a trial job beats the
     // incumbent by 3 % (or ties it with less host work); two failed trials halve the step and double the pause before
     // the next probe.  The state belongs to the (device, slot) and to the workload shape.
     bool tunable = false;
     HostPackMode hp_mode = decide_host_pack(plan, n_queries, query_len, slen, count, subjects->content + (size_t)first * (slen + 1), &tunable);
+    if (tunable && ranks_sharing_host() < 2 && !getenv("BGSA_HOST_PACK_TUNING")) tunable = false;   // alone on the host: the model holds
     double share = hp_mode == HP_ALWAYS ? 1.0 : (hp_mode == HP_NEVER ? 0.0 : -1.0);    // -1: live model of the measured rates (BGSA_HOST_PACK=2)
     Job::Tuner &tn = job.tuner;
     tn.armed = false;
@@ -878,20 +889,18 @@ static int submit_impl(const bgsa_params_t *p, const char *queries, int n_querie
         Lane &l = job.lane[li];
         bool host_pack = hp_mode == HP_ALWAYS;
         if (hp_mode == HP_HYBRID) {
-            // Share x of the chunks that cross the link as ASCII, dealt out by error diffusion (the first chunk goes over the
-            // link: the threads start on the second at once).  Tuned: x = 1 - share.  Live model (BGSA_HOST_PACK=2): link
-            // and threads finish together when  x Tl + (1-x) Tl/4 = (1-x) Tp  (Tl, Tp: measured link / pack time of a
-            // chunk)  =>  x = (Tp - Tl/4) / (Tp + 3 Tl/4).
-            double x = 1.0 - share;
             if (live_model) {
-                (void)link_backlog_s();                           // (reads the finished copies: updates link_rate)
-                const double tp = 1.0 / pack_rate, tl = 1.0 / link_rate;
-                x = (tp - 0.25 * tl) / (tp + 0.75 * tl);
+                // One rank on the host: decide chunk by chunk from the link's measured state -- pack while the copies
+                // already queued keep the link busy for at least half the time the threads need for this chunk, else
+                // feed the link (the first chunk goes over the link: the threads start on the second at once).
+                host_pack = link_backlog_s() > 0.5 * (double)n * (slen + 1) / pack_rate;
+            } else {
+                // Tuned share (several ranks on the host): 1 - share of the chunks cross the link as ASCII, dealt out by
+                // error diffusion.
+                ascii_credit += 1.0 - share;
+                host_pack = ascii_credit < 1.0;
+                if (!host_pack) ascii_credit -= 1.0;
             }
-            x = x < 0.0 ? 0.0 : (x > 1.0 ? 1.0 : x);
-            ascii_credit += x;
-            host_pack = ascii_credit < 1.0;
-            if (!host_pack) ascii_credit -= 1.0;
         }
         const bool fused = can_fuse && !host_pack;
         ChunkTrace tr{off, n, li, {nullptr, nullptr, nullptr, nullptr}, host_pack ? 1 : 0};

@@ -166,8 +166,11 @@ int bgsa_align_rows_device(const bgsa_params_t *p, const char *h_queries, int n_
                            void *d_results, int64_t result_stride, int device, void *stream);
 /* The front end of the last bgsa_align_batch[_submit] job on (device, slot): the share of its chunks that the host threads
  * packed (0 = every chunk crossed the link as ASCII, 1 = every chunk was packed on the host; -1 = decided chunk by chunk
- * from the measured rates, BGSA_HOST_PACK=2).  For pinned subjects the share is tuned job by job on the measured
- * throughput (BGSA_HOST_PACK_NO_TUNING=1 keeps the static model's choice; BGSA_HOST_PACK=0/1 forces it). */
+ * from the measured state of the link: what a rank alone on its host does when neither extreme wins).  When several ranks
+ * or devices share the host (torchrun's LOCAL_WORLD_SIZE, BGSA_HOST_GPUS, or several devices initialised by this process)
+ * and the subjects are pinned, the share is tuned job by job on the measured throughput of the jobs themselves
+ * (BGSA_HOST_PACK_NO_TUNING=1 keeps the static model's choice, BGSA_HOST_PACK_TUNING=1 tunes even alone;
+ * BGSA_HOST_PACK=0/1/2 forces never / always / chunk by chunk). */
 int bgsa_batch_front_end(int device, int slot, double *host_pack_share);
 /* Name of what bgsa_align_rows_device runs for these parameters; *fused = 1 when that is ONE kernel fed with the ASCII rows
  * (no pack launch, no packed buffer), 0 when it is the pack kernel followed by bgsa_align_device's kernel. */

@@ -75,6 +75,26 @@ def test_aligner_bitpal_and_semiglobal_sample(sample, golden_dir):
         assert md5(sample / "r_semi.txt") == "41696989c6d7e5f58897d81d154c47ea"     # the checked-in convert_result.txt
 
 
+def test_aligner_any_scoring_scheme(sample, tmp_path, monkeypatch):
+    """`aligner -a bitpal -M -I -G` with a scheme that is not built into the library: the reference would re-run its
+    generator and recompile (Main.java:240-315); here the instance is made at run time (csrc/jit.cu) -- same CLI, scores
+    equal to plain DP, result file readable by the reference's convert."""
+    monkeypatch.setenv("BGSA_JIT_CACHE", str(tmp_path / "jit"))
+    q, s = R.sample_data()
+    for name, algo, kind, (M, I, G) in (("bitpal", R.ALGO_BITPAL_PACKED, "nw", (4, -6, -10)),
+                                        ("bitpal-nonpacked", R.ALGO_BITPAL_PACKED, "nw", (1, -1, -2)),
+                                        ("bitpal-semiglobal", R.ALGO_BITPAL_SEMI, "nw_semi", (3, -2, -4))):
+        out = f"r_{name}_{M}.bin"
+        run([ALIGNER, "-a", name, "-M", str(M), "-I", str(I), "-G", str(G), "-q", "query.txt", "-d", "subject.txt", "-f", out], sample)
+        got = np.fromfile(sample / out, dtype=np.int16).reshape(3, 128)
+        assert (got == R.oracle_batch(algo, q, s, M=M, I=I, G=G)).all(), (name, M, I, G)
+        assert (got[:, :4] == R.dp_scores(kind, q, s[:4], M=M, I=I, G=G).astype(np.int16)).all()
+    assert len(list((tmp_path / "jit").glob("bgsa_*.bin"))) == 3
+    if (REF / "convert_int16").exists():
+        run([REF / "convert_int16", "-r", "r_bitpal_4.bin", "-o", "r_bitpal_4.txt"], sample)
+        assert len((sample / "r_bitpal_4.txt").read_text().split()) == 3 * 128
+
+
 def test_aligner_query_file_without_final_newline_and_m1(sample):
     q, _ = R.sample_data()
     R.write_rows(sample / "query_nonl.txt", q, final_newline=False)

@@ -645,6 +645,40 @@ def test_batch_entry_host_pack_front_end(B, force, monkeypatch):
     assert (B.align_batch(B.Params.default(B.BITPAL_PACKED), ql, sl) == R.oracle_batch(3, ql, sl)).all()
 
 
+def test_front_end_tuner_never_changes_scores(B, monkeypatch):
+    """The batch entry tunes, job by job, which share of the chunks the host threads pack (api.cu front end): whatever the
+    search tries -- all ASCII, all host-packed, any mix, trial jobs -- the scores are the same, and the share it reports
+    stays within [0, 1].  Also the forced modes and the untuned model."""
+    monkeypatch.delenv("BGSA_HOST_PACK", raising=False)
+    monkeypatch.setenv("BGSA_HOST_PACK_TUNING", "1")         # (a rank alone on its host keeps the static model: force the search on)
+    q, s = synth.make("C2", 60_000)
+    for algo, kw, oalgo in ((B.MYERS_GLOBAL, {}, 0), (B.BANDED_MYERS, {"threshold": 5}, 2)):
+        if algo == B.BANDED_MYERS:
+            q, s = synth.make("C3", 120_000)
+        p = B.Params.default(algo, **kw)
+        import torch
+        h = torch.from_numpy(s.reshape(-1)).pin_memory()
+        sp = h.numpy().reshape(s.shape)
+        exp = R.oracle_batch(oalgo, q, s[:20000], e=5)
+        seen = set()
+        for i in range(14):
+            got = B.align_batch(p, q, sp)
+            share = B.batch_front_end(0, 0)
+            assert 0.0 <= share <= 1.0
+            seen.add(round(share, 3))
+            assert (got[:, :20000] == exp).all(), (algo, i, share)
+        assert len(seen) >= 2, seen                       # the search really moved
+        for mode in ("0", "1", "2"):
+            monkeypatch.setenv("BGSA_HOST_PACK", mode)
+            assert (B.align_batch(p, q, sp)[:, :20000] == exp).all(), (algo, mode)
+            assert B.batch_front_end(0, 0) == {"0": 0.0, "1": 1.0, "2": -1.0}[mode]
+        monkeypatch.delenv("BGSA_HOST_PACK")
+        monkeypatch.setenv("BGSA_HOST_PACK_NO_TUNING", "1")
+        assert (B.align_batch(p, q, sp)[:, :20000] == exp).all()
+        assert B.batch_front_end(0, 0) in (0.0, 1.0, -1.0)   # the model's choice: never / always / chunk by chunk
+        monkeypatch.delenv("BGSA_HOST_PACK_NO_TUNING")
+
+
 def test_resident_entries_concurrent_streams_and_alignment(B):
     """bgsa_align_device from several host threads on several streams at once, each with its OWN queries: the
     query tables, work counters and packed scratch are per caller stream, so nothing is shared.  Misaligned
