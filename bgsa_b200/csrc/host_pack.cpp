@@ -65,6 +65,14 @@ inline void unit_scalar(const uint8_t *p, int left, bool planes, const uint8_t *
     *n0 = a.n; *n1 = b.n;
 }
 
+// dst (16-byte aligned: tiles start on 512-byte boundaries of a 256-byte aligned buffer) <- src, non-temporal (SSE2)
+inline void stream_out(uint32_t *dst, const uint32_t *src, size_t bytes) {
+    if (reinterpret_cast<uintptr_t>(dst) & 15) { memcpy(dst, src, bytes); return; }      // (caller's buffer not aligned: plain copy)
+    __m128i *d = reinterpret_cast<__m128i *>(dst);
+    const __m128i *s = reinterpret_cast<const __m128i *>(src);
+    for (size_t i = 0; i < bytes / 16; i++) _mm_stream_si128(d + i, _mm_load_si128(s + i));
+}
+
 // The tile loop, instantiated once per encoder (the AVX2 copy lives inside a `#pragma GCC target("avx2")` region so that
 // the intrinsics inline; the library itself is built for baseline x86-64 and picks at run time).
 #define BGSA_PACK_RANGE_BODY(UNIT)                                                                                       \
@@ -73,10 +81,14 @@ inline void unit_scalar(const uint8_t *p, int left, bool planes, const uint8_t *
     const int64_t stride = (int64_t)slen + 1;                                                                            \
     const uint8_t *end = rows + count * stride; /* one past the last byte that may be read */                           \
     std::vector<uint32_t> nbuf((size_t)v.kn * 32, 0u); /* N words of the current tile; all zero between tiles */         \
+    /* A tile is assembled in a cache-resident buffer and then streamed out with non-temporal stores: the destination  */ \
+    /* (pinned staging) is only read by the DMA engine afterwards, and a thread's speed is bound by the memory traffic */ \
+    /* it causes -- plain stores would first READ every destination line (write-allocate).                             */ \
+    std::vector<uint32_t> tbuf((size_t)v.ku * 32 * 4 + 16);                                                              \
+    uint32_t *tile_out = reinterpret_cast<uint32_t *>((reinterpret_cast<uintptr_t>(tbuf.data()) + 63) & ~(uintptr_t)63); \
     bool any = false;                                                                                                    \
     for (int64_t tile = t0; tile < t1; tile++) {                                                                         \
         uint32_t tile_n = 0u;                                                                                            \
-        uint32_t *tile_out = v.codes + tile * v.ku * 32 * 4;                                                             \
         for (int lane = 0; lane < 32; lane++) {                                                                          \
             const int64_t subject = tile * kTile + lane;                                                                 \
             if (subject >= count) {                                                                                      \
@@ -94,6 +106,7 @@ inline void unit_scalar(const uint8_t *p, int left, bool planes, const uint8_t *
                 }                                                                                                        \
             }                                                                                                            \
         }                                                                                                                \
+        stream_out(v.codes + tile * v.ku * 32 * 4, tile_out, (size_t)v.ku * 32 * 16);                                    \
         v.flags[tile] = tile_n ? 1 : 0;                                                                                  \
         if (tile_n) {                                                                                                    \
             memcpy(v.nmask + tile * v.kn * 32, nbuf.data(), sizeof(uint32_t) * (size_t)v.kn * 32);                       \
@@ -101,6 +114,7 @@ inline void unit_scalar(const uint8_t *p, int left, bool planes, const uint8_t *
             any = true;                                                                                                  \
         }                                                                                                                \
     }                                                                                                                    \
+    _mm_sfence(); /* the streamed tiles are globally visible before the caller hands the buffer to the copy engine */    \
     return any;
 
 bool pack_range_scalar(int layout, const uint8_t *rows, int slen, int64_t count, void *packed, int64_t t0, int64_t t1) {
@@ -167,8 +181,16 @@ bool pack_range_avx2(int layout, const uint8_t *rows, int slen, int64_t count, v
 }
 #pragma GCC pop_options
 
+// (An AVX-512 VBMI encoder -- one VPERMB lookup pair and three mask tests per 64 bases, PDEP interleave -- was written and
+//  measured: no faster than this one, 4.7 against 5.1 GB/s per thread.  A thread is bound by the memory traffic of its
+//  stream, about 10 GB/s of reads per core on these hosts, not by the encode; tools/host_pack_bench.py scales linearly
+//  with the threads up to the host's memory bandwidth.)
+// BGSA_HOST_PACK_ISA=scalar (or the older BGSA_HOST_PACK_SCALAR=1) forces the scalar twin (tests).
 bool cpu_has_avx2() {
-    static const bool has = __builtin_cpu_supports("avx2") && !getenv("BGSA_HOST_PACK_SCALAR");
+    static const bool has = [] {
+        const char *cap = getenv("BGSA_HOST_PACK_ISA");
+        return __builtin_cpu_supports("avx2") && !getenv("BGSA_HOST_PACK_SCALAR") && !(cap && !strcmp(cap, "scalar"));
+    }();
     return has;
 }
 
