@@ -692,7 +692,7 @@ static HostPackMode decide_host_pack(const Plan &plan, int nq, int qlen, int sle
     bool pinned = true;
     if (cudaPointerGetAttributes(&attr, rows) == cudaSuccess) pinned = attr.type != cudaMemoryTypeUnregistered;
     else cudaGetLastError();
-    const double t_pack = bytes / (HostPool::instance().threads() * 4.4e9);     // measured: 4.4-5 GB/s per thread inside the pipeline (DRAM-bound)
+    const double t_pack = bytes / (HostPool::instance().threads() * 6.0e9);     // measured: 6-8 GB/s per thread (bound by the thread's memory stream)
     const double t_link = bytes / kPcieBytesPerS;
     if (!pinned) return std::max(t_pack, t_kernel) < 0.9 * std::max(bytes / 9e9, t_kernel) ? HP_ALWAYS : HP_NEVER;
     if (t_kernel > 2.0 * t_link) return HP_NEVER;                                 // the link hides behind the kernel with room to spare: leave the host
@@ -784,7 +784,7 @@ static int submit_impl(const bgsa_params_t *p, const char *queries, int n_querie
             tn = Job::Tuner();
             tn.key = key;
             if (hp_mode == HP_HYBRID) {
-                const double tp = 1.0 / (HostPool::instance().threads() * 4.4e9), tl = 1.0 / kPcieBytesPerS;
+                const double tp = 1.0 / (HostPool::instance().threads() * 6.0e9), tl = 1.0 / kPcieBytesPerS;
                 tn.p = 1.0 - (tp - 0.25 * tl) / (tp + 0.75 * tl);
             } else {
                 tn.p = share;
@@ -844,7 +844,7 @@ static int submit_impl(const bgsa_params_t *p, const char *queries, int n_querie
     // hybrid bookkeeping, all MEASURED: the threads' pack rate, and the link's state read back from the lanes' copy events --
     // bytes still queued on the link and the rate at which the finished copies really moved (with several ranks on one
     // host the link delivers a fraction of its nominal rate: 184 GB/s for 8 GPUs together against 55 for one alone)
-    double pack_rate = HostPool::instance().threads() * 4.0e9, link_rate = job.link_rate > 0 ? job.link_rate : kPcieBytesPerS;
+    double pack_rate = HostPool::instance().threads() * 6.0e9, link_rate = job.link_rate > 0 ? job.link_rate : kPcieBytesPerS;
     // A copy's own duration = from the later of (its begin event, the end of the copy queued before it) to its end: the
     // lanes' copies share one engine, so a copy queued behind another would otherwise look slow.
     auto link_backlog_s = [&]() {
@@ -891,9 +891,11 @@ static int submit_impl(const bgsa_params_t *p, const char *queries, int n_querie
         if (hp_mode == HP_HYBRID) {
             if (live_model) {
                 // One rank on the host: decide chunk by chunk from the link's measured state -- pack while the copies
-                // already queued keep the link busy for at least half the time the threads need for this chunk, else
-                // feed the link (the first chunk goes over the link: the threads start on the second at once).
-                host_pack = link_backlog_s() > 0.5 * (double)n * (slen + 1) / pack_rate;
+                // already queued keep the link busy for the time the threads need for this chunk, else feed the link
+                // (the first chunk goes over the link: the threads start on the second at once).  Factor swept on the
+                // B200 box (profiles/r02_e2e_hybrid_factor.log): 1.0 beats 0.5 / 0.25 / 0.1 on C3 and Myers 150 bp.
+                static const double kF = getenv("BGSA_HYBRID_F") ? atof(getenv("BGSA_HYBRID_F")) : 1.0;      // A/B knob
+                host_pack = link_backlog_s() > kF * (double)n * (slen + 1) / pack_rate;
             } else {
                 // Tuned share (several ranks on the host): 1 - share of the chunks cross the link as ASCII, dealt out by
                 // error diffusion.

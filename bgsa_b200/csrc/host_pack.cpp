@@ -148,7 +148,14 @@ inline __m256i classify(__m256i v) {
     const __m256i lo = _mm256_and_si256(v, nib), hi = _mm256_and_si256(_mm256_srli_epi16(v, 4), nib);
     return _mm256_and_si256(_mm256_shuffle_epi8(lut_lo, lo), _mm256_shuffle_epi8(lut_hi, hi));
 }
+#ifndef BGSA_PREFETCH_AHEAD
+#define BGSA_PREFETCH_AHEAD 2048
+#endif
+// Bytes ahead of the unit being encoded (the rows of a range are one ascending stream).  The hardware prefetcher of these
+// (virtualised) hosts leaves a thread at 4-5 GB/s; with a software prefetch 1.5-4 KB ahead it reaches 6-9 (sweep: 2 KB).
+constexpr int kPrefetchAhead = BGSA_PREFETCH_AHEAD;
 inline void unit_avx2(const uint8_t *p, int left, bool planes, const uint8_t *end, uint32_t *out, uint32_t *n0, uint32_t *n1) {
+    _mm_prefetch(reinterpret_cast<const char *>(p) + kPrefetchAhead, _MM_HINT_T0);
     const __m256i A = load_valid(p, left, end);
     const __m256i B = left > 32 ? load_valid(p + 32, left - 32, end) : _mm256_setzero_si256();
     const __m256i xa = classify(A), xb = classify(B);
