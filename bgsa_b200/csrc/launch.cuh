@@ -64,7 +64,7 @@ cudaError_t launch_align(const LaunchArgs &a, typename Algo::Params prm) {
 }
 
 // ---- rows kernel (rows_kernel.cuh): thread-per-subject straight from the ASCII rows ------------------------------------
-constexpr int kRowsMaxK = 8;                     // mask table by byte value: 256 x 12 words = 12 KB up to K = 8
+constexpr int kRowsMaxK = 12;                    // mask table by byte value: 256 x 12 words = 12 KB up to K = 12 (queries up to 384 bases)
 constexpr int kRowsMaxStageBytes = 13 * 1024;    // one tile of rows of up to ~400 bases
 inline bool rows_kernel_fits(int K, int L, int slen) {
     const bool off = getenv("BGSA_NO_ROWS_KERNEL") != nullptr;               // A/B knob (read per call: the tests flip it): always pack + align

@@ -15,7 +15,7 @@
 // ALU-pipe cost per column: that of the DP recurrence alone (Myers K=5: 49.3 instead of 51.3 + the pack kernel).
 // HBM traffic per subject: slen+1 bytes in, 2 out (instead of slen/4 in after a pack pass that read slen+1 anyway).
 //
-// Restrictions (host side: rows_kernel_fits): L = 1 instances with a small mask table (K <= 8), a tile that fits the
+// Restrictions (host side: rows_kernel_fits): L = 1 instances with a small mask table (K <= 12), a tile that fits the
 // stage (rows up to ~400 bases), and a row pitch whose 32 lanes do not pile up on a few shared-memory banks (a pitch
 // that is a multiple of 64 bytes would serialise every byte load; such sets take the pack + align path).
 #pragma once

@@ -158,7 +158,7 @@ int bgsa_align_device(const bgsa_params_t *p, const char *h_queries, int n_queri
                       void *d_results, int64_t result_stride, int device, void *stream);
 /* d_rows: device pointer to ASCII rows (stride subject_len+1), as bgsa_pack_subjects_device takes them; scores to
  * d_results.  ONE kernel where the rows are short enough for a warp's shared-memory stage: banded Myers on rows up to ~950
- * bases (encodes every tile into shared memory and verifies it in place), Myers / BitPAl on queries up to 256 bases and rows
+ * bases (encodes every tile into shared memory and verifies it in place), Myers / BitPAl on queries up to 384 bases and rows
  * up to ~400 (thread per subject, match masks looked up by byte value: rows_kernel.cuh); otherwise packs into a
  * library-owned buffer and aligns.  bgsa_rows_kernel_name tells which. */
 int bgsa_align_rows_device(const bgsa_params_t *p, const char *h_queries, int n_queries, int query_len,

@@ -491,7 +491,7 @@ def test_rows_device_entry_other_algorithms(B):
 
 
 @pytest.mark.parametrize("ql,sl,n", [(150, 150, 4099), (100, 100, 1000), (64, 37, 333), (256, 250, 700), (33, 400, 97), (1, 9, 70),
-                                     (150, 151, 64), (200, 135, 31), (96, 15, 65), (250, 303, 2049)])
+                                     (150, 151, 64), (200, 135, 31), (96, 15, 65), (250, 303, 2049), (330, 300, 200), (384, 250, 97)])
 def test_rows_kernel_every_algorithm(B, ql, sl, n, monkeypatch):
     """align_rows_kernel (rows_kernel.cuh): thread per subject straight from the ASCII rows, match masks looked up by byte
     value.  Against the oracle and against the pack + align path, for every algorithm that has it; rows with N, lower
@@ -551,7 +551,8 @@ def test_rows_kernel_eligibility(B):
     assert not B.rows_kernel_name(p, 150, 127)[1]        # pitch 128: every lane on the same bank
     assert not B.rows_kernel_name(p, 150, 63)[1]
     assert not B.rows_kernel_name(p, 150, 1000)[1]       # a tile does not fit the stage
-    assert not B.rows_kernel_name(p, 300, 150)[1]        # K > 8: no rows instance
+    assert B.rows_kernel_name(p, 384, 150)[1]            # 12 words: the largest rows instance
+    assert not B.rows_kernel_name(p, 500, 150)[1]        # K > 12: no rows instance
     rng = np.random.default_rng(3)
     q = R.random_rows(rng, 1, 150); s = R.random_rows(rng, 500, 127, with_n=0.01)
     assert (B.align_batch(p, q, s) == R.oracle_batch(0, q, s)).all()
