@@ -700,7 +700,11 @@ static HostPackMode decide_host_pack(const Plan &plan, int nq, int qlen, int sle
     *tunable = getenv("BGSA_HOST_PACK_NO_TUNING") == nullptr;
     if (t_pack <= 0.9 * t_kernel) return HP_ALWAYS;                               // the threads stay ahead of the kernel: the link is nearly free
     if (t_kernel > 1.15 * t_link) return HP_NEVER;                                // they cannot, and the link hides behind the kernel anyway
-    return t_pack < 4.0 * t_link ? HP_HYBRID : HP_NEVER;                          // threads too few to matter: leave them alone
+    // The pool must at least come near the link's rate (6 threads and more).  With fewer -- 8 ranks on a 32-core host -- the
+    // DMA engines of all the GPUs together already saturate the host's memory (182 GB/s) and every byte the threads touch
+    // only adds traffic: any share of host packing LOSES there, tuned or not (profiles/r02_e2e_multi_rank.log).
+    if (t_pack >= 1.5 * t_link) { *tunable = false; return HP_NEVER; }
+    return HP_HYBRID;
 }
 // Ranks (processes or devices of this process) that pull subjects through this host at the same time: torchrun's
 // LOCAL_WORLD_SIZE / BGSA_HOST_GPUS, or the device contexts this process has brought up.
