@@ -668,7 +668,8 @@ def test_front_end_tuner_never_changes_scores(B, monkeypatch):
             assert 0.0 <= share <= 1.0
             seen.add(round(share, 3))
             assert (got[:, :20000] == exp).all(), (algo, i, share)
-        assert len(seen) >= 2, seen                       # the search really moved
+        if B.host_pack_info()[0] >= 6:                    # (a pool too small to matter is never used: nothing to search)
+            assert len(seen) >= 2, seen                   # the search really moved
         for mode in ("0", "1", "2"):
             monkeypatch.setenv("BGSA_HOST_PACK", mode)
             assert (B.align_batch(p, q, sp)[:, :20000] == exp).all(), (algo, mode)

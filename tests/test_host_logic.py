@@ -177,6 +177,28 @@ print('ok')
     assert res.returncode == 0 and "ok" in res.stdout, (res.returncode, res.stderr[-2000:])
 
 
+def test_rows_kernel_selection_needs_no_gpu():
+    """Which short-read geometries get the one-kernel path (rows_kernel.cuh: ASCII tile by bulk copy, masks by byte value)
+    is decided on the host: thread-per-subject instances up to 12 words, a tile that fits the stage, a row pitch whose 32
+    lanes do not pile up on a few shared-memory banks.  Everything else is pack + align; banded has its own fused kernel."""
+    import bgsa_b200 as B
+    _ensure_built()
+    my = B.Params.default(B.MYERS_GLOBAL)
+    assert B.rows_kernel_name(my, 150, 150) == ("align_rows_kernel<MyersAlgo<K=5,global>>", True)
+    assert B.rows_kernel_name(B.Params.default(B.BITPAL_PACKED), 150, 150) == ("align_rows_kernel<BitpalPacked<2,-3,-5,K=5>>", True)
+    assert B.rows_kernel_name(B.Params.default(B.BITPAL_NONPACKED), 150, 150)[1]
+    assert B.rows_kernel_name(B.Params.default(B.BITPAL_PACKED_SEMIGLOBAL), 100, 300)[1]
+    assert B.rows_kernel_name(my, 384, 250)[1] and not B.rows_kernel_name(my, 385, 250)[1]          # 12 words
+    name, fused = B.rows_kernel_name(my, 150, 1000)                                                 # tile too large for the stage
+    assert not fused and name == "pack_stream_kernel + align_kernel<MyersAlgo<K=5,global>,L=1>"
+    for slen, ok in ((127, False), (63, False), (191, False), (255, False), (100, True), (101, True), (151, True), (135, True), (250, True)):
+        assert B.rows_kernel_name(my, 100, slen)[1] == ok, slen                                     # pitch = slen + 1
+    assert not B.rows_kernel_name(B.Params.default(B.BITPAL_PACKED), 5000, 150)[1]                  # wavefront instance
+    name, fused = B.rows_kernel_name(B.Params.default(B.BANDED_MYERS, threshold=5), 100, 100)
+    assert fused and name.startswith("banded_kernel<u32> (fused")
+    assert not B.rows_kernel_name(B.Params.default(B.BANDED_MYERS, threshold=5), 1000, 1000)[1]
+
+
 def test_jit_precompile_needs_no_gpu(tmp_path, monkeypatch):
     """Scoring schemes outside the compiled list are instantiated by NVRTC from the kernel headers embedded in the library
     (csrc/jit.cu; the run-time counterpart of the reference's generator, Main.java:240-315).  The compile itself needs no
