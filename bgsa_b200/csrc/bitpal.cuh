@@ -129,18 +129,22 @@ struct BitpalPacked {
         uint32_t D[NH > 1 ? NH : 1][K];
 #pragma unroll
         for (int j = 0; j < K; j++) {
-            uint32_t hiz = 0xffffffffu;                      // planes 2.. all zero  <=>  d < 4
+            // hin = some plane above bit 1 is set  <=>  d >= 4.  Kept in this polarity: the tables below take its complement
+            // for free, whereas "all zero" would cost a NOT that the explicit tables keep the compiler from folding away
+            // (one LOP3 per word-column; profiles/r02_sass).
+            uint32_t hin = 0u;
 #pragma unroll
-            for (int b = 2; b < NB; b++) hiz &= ~s.d[b][j];
+            for (int b = 2; b < NB; b++) hin |= s.d[b][j];
+            constexpr int NA = 0xFF ^ LA;
             const uint32_t d0 = s.d[0][j], d1 = NB > 1 ? s.d[1][j] : 0u;
-            Z[j] = lop3<LA & (0xFF ^ LB) & (0xFF ^ LC)>(hiz, d1, d0);
+            Z[j] = lop3<NA & (0xFF ^ LB) & (0xFF ^ LC)>(hin, d1, d0);
             remain[j] = Z[j] & ~eq[j];                       // d == 0 and mismatch: runs that propagate
 #pragma unroll
             for (int v = 1; v < NH; v++) {
                 uint32_t m;
-                if (v == 1) m = lop3<LA & (0xFF ^ LB) & LC>(hiz, d1, d0);
-                else if (v == 2) m = lop3<LA & LB & (0xFF ^ LC)>(hiz, d1, d0);
-                else if (v == 3) m = lop3<LA & LB & LC>(hiz, d1, d0);
+                if (v == 1) m = lop3<NA & (0xFF ^ LB) & LC>(hin, d1, d0);
+                else if (v == 2) m = lop3<NA & LB & (0xFF ^ LC)>(hin, d1, d0);
+                else if (v == 3) m = lop3<NA & LB & LC>(hin, d1, d0);
                 else {
                     m = 0xffffffffu;
 #pragma unroll
