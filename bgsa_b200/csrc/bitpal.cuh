@@ -364,14 +364,17 @@ struct BitpalNonPacked {
                 }
             }
         }
-        uint32_t rest[K], xhi[K];                             // xhi = [B < e_{p-1} < A], shared with X0 below
+        // (rest, X0 and max(w,d) == B below are complements of ORs that feed explicit LOP3 tables: they are kept as the ORs --
+        //  nrest, nX0, nmxB -- and the tables take the complement, which saves the three NOTs per word that the compiler
+        //  cannot fold across the asm statements)
+        uint32_t nrest[K], xhi[K];                            // xhi = [B < e_{p-1} < A], shared with nX0 below
 #pragma unroll
         for (int j = 0; j < K; j++) {
             uint32_t any = 0u;
 #pragma unroll
             for (int k = A - 1; k > B; k--) any |= X[k][j];
             xhi[j] = any;
-            rest[j] = ~(any | Yh[A][j]);
+            nrest[j] = any | Yh[A][j];
         }
         // low classes 1..B: e_p == k  <=>  y_p - d_p == k ; no propagation, plain shift
 #pragma unroll
@@ -382,7 +385,7 @@ struct BitpalNonPacked {
                 uint32_t v = DV(A - k, j) & Yh[A][j];
 #pragma unroll
                 for (int h = A - 1; h > B; h--) v = lop3<LA | (LB & LC)>(v, DV(h - k, j), Yh[h][j]);
-                init[j] = lop3<LA | (LB & LC)>(v, DV(B - k, j), rest[j]);
+                init[j] = lop3<LA | (LB & (0xFF ^ LC))>(v, DV(B - k, j), nrest[j]);
             }
             const uint32_t sin = CARRY ? in.top() : 0u;
             if (CARRY) out.push_top(init[K - 1]);
@@ -391,13 +394,13 @@ struct BitpalNonPacked {
         }
 #undef DV
         // X0 = [e_{p-1} == 0]
-        uint32_t X0[K];
+        uint32_t nX0[K];
 #pragma unroll
         for (int j = 0; j < K; j++) {
             uint32_t any = xhi[j] | X[A][j];
 #pragma unroll
             for (int k = 1; k <= B; k++) any |= X[k][j];
-            X0[j] = ~any;
+            nX0[j] = any;
         }
         // Mx(v) = [max(w, d) == v]: v == A -> d==A | match ; B < v < A -> d==v & ~match ; v == B -> others
         // d'_k = OR_{m >= max(k,B)} Mx(m) & [e_{p-1} == m - k]      (k >= 1)
@@ -407,14 +410,21 @@ struct BitpalNonPacked {
             mx[A] = s.d[A - 1][j] | eq[j];
 #pragma unroll
             for (int v = A - 1; v > B; v--) mx[v] = s.d[v - 1][j] & ~eq[j];
-            mx[B] = ~(dhi[j] | eq[j]);                       // neither a match nor d > B
+            mx[B] = dhi[j] | eq[j];                          // COMPLEMENT of [max(w,d) == B]: a match or d > B
             uint32_t nd[A];
 #pragma unroll
             for (int k = 1; k <= A; k++) {
                 uint32_t v = 0u;
 #pragma unroll
                 for (int m = (k > B ? k : B); m <= A; m++)
-                    v = lop3<LA | (LB & LC)>(v, mx[m], (m - k) == 0 ? X0[j] : X[(m - k) > 0 ? (m - k) : 1][j]);
+                {
+                    const uint32_t xv = (m - k) == 0 ? nX0[j] : X[(m - k) > 0 ? (m - k) : 1][j];
+                    // v | (mx & x), with mx complemented for m == B and x complemented for m == k
+                    if (m == B && m == k) v = lop3<LA | ((0xFF ^ LB) & (0xFF ^ LC))>(v, mx[m], xv);
+                    else if (m == B) v = lop3<LA | ((0xFF ^ LB) & LC)>(v, mx[m], xv);
+                    else if (m == k) v = lop3<LA | (LB & (0xFF ^ LC))>(v, mx[m], xv);
+                    else v = lop3<LA | (LB & LC)>(v, mx[m], xv);
+                }
                 nd[k - 1] = v;
             }
 #pragma unroll
