@@ -209,18 +209,21 @@ struct BitpalPacked {
             // (explicit 3-input tables: left to itself the compiler materialises y ^ d and spends a third
             //  instruction per plane)
             constexpr int kBorrow = ((0xFF ^ LA) & LB) | ((0xFF ^ (LA ^ LB)) & LC);   // borrow out of a - b - c
-            uint32_t diff[NB], br = 0u;
+            // (top plane: the difference bit is only ever used masked by "no final borrow", and that borrow is a function of
+            //  the same three inputs -- one table gives the masked bit directly: one LOP3 less per word)
+            uint32_t diff[NB], br = 0u, e_top = 0u;
 #pragma unroll
             for (int b = 0; b < NB; b++) {
                 const uint32_t yb = y[b], db = s.d[b][j];
                 if (b == 0) { diff[b] = yb ^ db; br = ~yb & db; }
+                else if (b == NB - 1) { e_top = lop3<(LA ^ LB ^ LC) & (0xFF ^ kBorrow)>(yb, db, br); diff[b] = 0u; br = lop3<kBorrow>(yb, db, br); }
                 else { diff[b] = lop3<LA ^ LB ^ LC>(yb, db, br); br = lop3<kBorrow>(yb, db, br); }
             }
             const uint32_t lt = br;                           // y < d
             uint32_t e[NB], T[NB];
 #pragma unroll
             for (int b = 0; b < NB; b++) {
-                e[b] = diff[b] & ~lt;
+                e[b] = (b == NB - 1 && b > 0) ? e_top : (diff[b] & ~lt);
                 T[b] = lop3<(LA & LB) | ((0xFF ^ LA) & LC)>(lt, s.d[b][j], y[b]);
             }
             if (SEMI) {                                      // branch-free: one LOP3 per plane and word
