@@ -253,10 +253,10 @@ def test_sass_carry_chains_and_budget():
     sys.path.insert(0, str(ROOT / "tools"))
     import sass_budget as SB
     funcs = SB.sass_functions(ROOT / "bgsa_b200" / "libbgsa_b200.so")
-    expect = {"C2_bitpal_packed_K5": (5, 5, 66.0), "C4_myers_semi_K32": (1, 32, 10.3), "myers150_K5": (1, 5, 10.2),
-              "bitpal_nonpacked_150": (5, 5, 162.0),
+    expect = {"C2_bitpal_packed_K5": (5, 5, 63.0), "C4_myers_semi_K32": (1, 32, 10.3), "myers150_K5": (1, 5, 10.2),
+              "bitpal_nonpacked_150": (5, 5, 157.0),
               # the rows kernels (ASCII in, masks by byte value): the recurrence alone, word 0's shifts on the FMA pipe
-              "C2_rows_bitpal_packed_K5": (5, 5, 65.0), "myers150_rows_K5": (1, 5, 9.8), "C2np_rows_K5": (5, 5, 160.0)}
+              "C2_rows_bitpal_packed_K5": (5, 5, 62.5), "myers150_rows_K5": (1, 5, 9.8), "C2np_rows_K5": (5, 5, 156.0)}
     for name, (chains, K, max_alu_per_word) in expect.items():
         r = SB.analyse(name, SB.KERNELS[name], funcs, None)
         assert "error" not in r, (name, r)
