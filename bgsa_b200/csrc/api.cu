@@ -796,6 +796,7 @@ static int submit_impl(const bgsa_params_t *p, const char *queries, int n_querie
             share = tn.p;
         } else {
             auto clamp01 = [](double v) { return v < 0.0 ? 0.0 : (v > 1.0 ? 1.0 : v); };
+            tn.trial = false;                           // (a job whose wait never evaluated it leaves no stale trial behind)
             if (tn.hold > 0) {
                 tn.hold--;
                 share = tn.p;
