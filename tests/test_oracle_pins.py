@@ -78,10 +78,14 @@ def test_dp_equivalence_random():
         s[:3, : min(ql, sl)] = q[0, : min(ql, sl)]
         assert (R.oracle_batch(R.ALGO_MYERS_GLOBAL, q, s) == -R.dp_scores("edit", q, s)).all()
         assert (R.oracle_batch(R.ALGO_MYERS_SEMIGLOBAL, q, s) == -R.dp_scores("semi", q, s)).all()
-        for M, I, G in ((2, -3, -5), (1, -1, -1), (1, -3, -2), (4, -6, -10), (5, -4, -3)):
+        # every scheme the GPU tier runs: the three built in, and those instantiated at run time
+        # (tests/test_gpu_parity.py JIT_SCHEMES: the edit special case, common factors 2 and 5, wide and narrow delta ranges)
+        for M, I, G in ((2, -3, -5), (1, -1, -1), (1, -3, -2), (4, -6, -10), (5, -4, -3), (0, -1, -1), (5, -3, -4), (1, -1, -2),
+                        (3, -2, -4), (2, -1, -1), (1, -2, -3), (6, -1, -7), (10, -15, -25)):
             dp = R.dp_scores("nw", q, s, M, I, G)
             assert (R.oracle_batch(R.ALGO_BITPAL_PACKED, q, s, M=M, I=I, G=G) == dp).all(), (M, I, G)
             assert (R.oracle_batch(R.ALGO_BITPAL_NONPACKED, q, s, M=M, I=I, G=G) == dp).all(), (M, I, G)
+            assert (R.oracle_batch(R.ALGO_BITPAL_SEMI, q, s, M=M, I=I, G=G) == R.dp_scores("nw_semi", q, s, M, I, G)).all(), (M, I, G)
 
 
 def test_int16_wrap_like_reference():
