@@ -2,9 +2,11 @@
 #include "host_pack.h"
 
 #include <immintrin.h>
+#include <sched.h>
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <atomic>
 #include <condition_variable>
 #include <mutex>
@@ -266,6 +268,13 @@ static int pool_default_threads() {
     if (const char *g = getenv("BGSA_HOST_GPUS")) share = atoi(g) >= 1 ? atoi(g) : 1;
     else if (const char *w = getenv("LOCAL_WORLD_SIZE")) share = atoi(w) >= 1 ? atoi(w) : 1;     // torchrun: ranks on this host
     int t = (int)hw / share;
+    // never more threads than CPUs this thread may run on (taskset, cgroup cpusets, bgsa_bind_thread_to_device: the workers
+    // inherit the creating thread's affinity mask, and two workers per allowed CPU only slow each other down)
+    cpu_set_t allowed;
+    if (sched_getaffinity(0, sizeof(allowed), &allowed) == 0) {
+        const int n = CPU_COUNT(&allowed);
+        if (n >= 1 && n < (int)hw) t = std::min(t, std::max(1, n));
+    }
     if (t < 1) t = 1;
     return t > 64 ? 64 : t;
 }

@@ -242,6 +242,26 @@ print('ok')
     assert res.returncode == 0 and "ok" in res.stdout, res.stderr
 
 
+def test_host_pool_respects_cpu_affinity():
+    """The worker pool is sized by the CPUs its creator may run on, not by the machine: under taskset / a cpuset / after
+    bgsa_bind_thread_to_device the workers inherit the mask, and more workers than allowed CPUs only slow each other down."""
+    if not hasattr(os, "sched_setaffinity") or len(os.sched_getaffinity(0)) < 2:
+        pytest.skip("needs at least two allowed CPUs")
+    _ensure_built()
+    code = """
+import os, sys
+sys.path.insert(0, %r)
+cpus = sorted(os.sched_getaffinity(0))[:2]
+os.sched_setaffinity(0, set(cpus))
+import bgsa_b200 as B
+print('threads', B.host_pack_info()[0])
+""" % str(ROOT)
+    env = {k: v for k, v in os.environ.items() if k not in ("BGSA_HOST_THREADS", "BGSA_HOST_GPUS", "LOCAL_WORLD_SIZE")}
+    res = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=120)
+    assert res.returncode == 0, res.stderr
+    assert int(res.stdout.split()[-1]) in (1, 2), res.stdout
+
+
 def test_sass_carry_chains_and_budget():
     """Build-time guard for the hardware carry chains (bgsa_common.cuh add_chain: consecutive add.cc / addc.cc asm
     statements rely on nothing clobbering CC.CF in between): in the SASS of the thread-per-subject kernels every
